@@ -1,0 +1,137 @@
+/*
+ * mnb200.h -- C ABI of libmnb200.so: hand-written sm_100a CUDA kernels for the MNASNet training step
+ * of snakers4/mnasnet-pytorch (forward / backward / optimizer), NHWC activations.
+ *
+ * The reference has no FFI of its own; the boundary it exposes is the torch operator API reached from
+ *   src/models/mnasnet.py:37-62   ConvBlock  = nn.Conv2d(bias) -> nn.BatchNorm2d -> nn.ReLU
+ *   src/models/mnasnet.py:131-133 MBConv_block residual add
+ *   src/models/classifiers.py:107-111 AdaptiveAvgPool2d(1) -> Dropout/Linear/ReLU head
+ *   src/train.py:277,435-440      CrossEntropyLoss, backward, Adam.step
+ * Every entry point below names the reference call it replaces.  See INTEGRATION.md for the ctypes
+ * binding used by the drop-in `models/` package.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer owned by the caller; the library keeps
+ *     no reference after the call returns and allocates nothing (except a per-process weight scratch, see
+ *     mnb_gemm_workspace_bytes).
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*); no implicit sync.
+ *   - return value: 0 ok; <0 argument error (MNB_ERR_*); >0 cudaError_t.  Message: mnb_last_error().
+ *   - activations: NHWC, dtype MNB_F32 or MNB_BF16, C % 8 == 0 (except the NCHW fp32 network input);
+ *     parameters, gradients of parameters, BN vectors: fp32; BN statistics accumulators: fp64.
+ *   - "x-transform": when in_scale != NULL the kernel reads  a = max(in_scale[c]*x + in_shift[c], 0)
+ *     (the previous ConvBlock's BN-apply + ReLU fused into the load); NULL -> x is used as is.
+ *   - stats: double[2*C] = {sum z, sum z^2} per channel, ACCUMULATED (caller zeroes before the layer).
+ */
+#ifndef MNB200_H
+#define MNB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNB_F32 0
+#define MNB_BF16 1
+
+#define MNB_ERR_ARG (-1)        /* bad shape / alignment / dtype */
+#define MNB_ERR_UNSUPPORTED (-2)
+
+#define MNB_LAYOUT_NHWC 0
+#define MNB_LAYOUT_NCHW_F32 1   /* network input: N x C x H x W fp32 (train.py:427) */
+
+int mnb_version(void);
+const char* mnb_last_error(void);
+/* 1 if the running device is sm_100 (tcgen05 path usable) */
+int mnb_device_is_sm100(void);
+
+/* ---- dense convolution (groups=1; k in {1,3}; stride in {1,2}) : nn.Conv2d, mnasnet.py:48-54 -------------
+ * z[n,ho,wo,co] = bias[co] + sum_{kh,kw,ci} a(n, ho*stride-pad+kh, wo*stride-pad+kw, ci) * w[co,ci,kh,kw]
+ * w is the torch layout [Cout,Cin,k,k] fp32.  x_layout selects NHWC(dtype) or NCHW fp32 (stem only).
+ * impl: 0 = auto (tcgen05 for bf16 where available), 1 = force SIMT, 2 = force tcgen05. */
+int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w, const float* bias,
+                 void* z, double* stats, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                 int dtype, int x_layout, int impl, void* stream);
+/* dx[n,h,w,ci] = (add ? add[n,h,w,ci] : 0) + sum dz[n,ho,wo,co]*w[co,ci,kh,kw]   (conv backward-data) */
+int mnb_conv_dgrad(const void* dz, const float* w, const void* add, void* dx, int N, int H, int W, int Cin,
+                   int Cout, int k, int stride, int pad, int dtype, int impl, void* stream);
+/* dw[co,ci,kh,kw] += sum a(...)*dz[...]  (conv backward-weight; fp32 accumulate INTO dw) */
+int mnb_conv_wgrad(const void* x, const float* in_scale, const float* in_shift, const void* dz, float* dw,
+                   int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dtype, int x_layout,
+                   int impl, void* stream);
+
+/* ---- depthwise convolution k in {3,5}, stride 1, pad k/2 : nn.Conv2d(groups=C), mnasnet.py:76-81,120-125 -- */
+int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w /*[C,1,k,k]*/,
+               const float* bias, void* z, double* stats, int N, int H, int W, int C, int k, int dtype,
+               void* stream);
+int mnb_dw_dgrad(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, int dtype,
+                 void* stream);
+int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, const void* dz, float* dw,
+                 int N, int H, int W, int C, int k, int dtype, void* stream);
+
+/* ---- BatchNorm2d (train) : mnasnet.py:55,60 ; torch:nn/modules/batchnorm.py:163-178 ----------------------
+ * finalize: mean/var from stats over m positions -> scale = gamma/sqrt(var+eps), shift = beta-mean*scale,
+ * saves mean & invstd, updates running stats (unbiased var, momentum) and num_batches_tracked (+1) if given. */
+int mnb_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, float* scale, float* shift,
+                    float* save_mean, float* save_invstd, int C, double m, float eps, float momentum,
+                    void* stream);
+/* eval mode: scale/shift from running stats */
+int mnb_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float* scale, float* shift, int C, float eps, void* stream);
+/* y = (residual ? residual : 0) + max(scale*z+shift, 0)     (BN-apply + ReLU + MBConv_block skip add) */
+int mnb_bn_relu_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y,
+                      long long M, int C, int dtype, void* stream);
+/* backward reductions: sums[0:C] += sum G, sums[C:2C] += sum G*z with G = dA*[scale*z+shift>0] */
+int mnb_bn_bwd_reduce(const void* dA, const void* z, const float* scale, const float* shift, double* sums,
+                      long long M, int C, int dtype, void* stream);
+/* dgamma += , dbeta += , dbias += (analytically 0), coef[3C] = {a,b,c} with dZ = a*G + b*z + c */
+int mnb_bn_bwd_finalize(const double* sums, const float* scale, const float* save_mean,
+                        const float* save_invstd, float* dgamma, float* dbeta, float* dbias, float* coef, int C,
+                        double m, void* stream);
+/* dZ = a*G + b*z + c  (materialised) */
+int mnb_bn_bwd_apply(const void* dA, const void* z, const float* scale, const float* shift, const float* coef,
+                     void* dZ, long long M, int C, int dtype, void* stream);
+
+/* ---- head : classifiers.py:107-111 -------------------------------------------------------------------- */
+/* f[n,c] = mean_hw max(scale*z+shift,0)  (fp32 out)  : AdaptiveAvgPool2d(1) fused with the last BN+ReLU */
+int mnb_gap_fwd(const void* z, const float* scale, const float* shift, float* f, int N, int HW, int C,
+                int dtype, void* stream);
+/* dA[n,hw,c] = df[n,c]/HW */
+int mnb_gap_bwd(const float* df, void* dA, int N, int HW, int C, int dtype, void* stream);
+/* Bernoulli keep-mask (1 = keep) with prob 1-p from a counter-based RNG (seed, offset) : nn.Dropout.
+ * dev_step (nullable, device): element i uses counter offset + (*dev_step)*n + i, so a captured CUDA graph
+ * draws fresh masks on every replay. */
+int mnb_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed,
+                     unsigned long long offset, const long long* dev_step, void* stream);
+/* y[n,o] = b[o] + sum_k (x[n,k]*mask[n,k]*mask_scale) * w[o,k] ; relu_out -> y = max(y,0)  : nn.Linear */
+int mnb_fc_fwd(const float* x, const unsigned char* mask, float mask_scale, const float* w, const float* b,
+               float* y, int relu_out, int N, int K, int O, void* stream);
+/* dx[n,k] = (sum_o dy[n,o]*w[o,k]) * mask[n,k]*mask_scale * (relu_ref ? relu_ref[n,k]>0 : 1) */
+int mnb_fc_dgrad(const float* dy, const float* w, const unsigned char* mask, float mask_scale,
+                 const float* relu_ref, float* dx, int N, int K, int O, void* stream);
+/* dw[o,k] += sum_n dy[n,o]*x[n,k]*mask*mask_scale ; db[o] += sum_n dy[n,o] */
+int mnb_fc_wgrad(const float* x, const unsigned char* mask, float mask_scale, const float* dy, float* dw,
+                 float* db, int N, int K, int O, void* stream);
+
+/* ---- loss : nn.CrossEntropyLoss(mean), train.py:277,435 --------------------------------------------------
+ * loss[0] += mean_n( -log softmax(logits_n)[target_n] ) (caller zeroes loss);
+ * dlogits (nullable) = (softmax - onehot) * grad_scale / N */
+int mnb_xent_fwd_bwd(const float* logits, const long long* target, float* loss, float* dlogits, int N, int O,
+                     float grad_scale, void* stream);
+
+/* ---- optimizer : torch.optim.Adam defaults, train.py:219-221,440 (flat buffers) ------------------------ */
+/* dev_lr / dev_step (nullable, device scalars) override lr / step so that a captured CUDA graph follows the
+ * host-side LR schedule (train.py:282-302,334) and step count without re-capture. */
+int mnb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, int step, float grad_scale, const float* dev_lr, const long long* dev_step,
+                  void* stream);
+/* *counter += 1 on the device (step counter feeding mnb_adam_step / mnb_dropout_mask inside a graph) */
+int mnb_counter_inc(long long* counter, void* stream);
+
+/* ---- layout helpers --------------------------------------------------------------------------------- */
+int mnb_nhwc_to_nchw_f32(const void* x, float* y, int N, int H, int W, int C, int dtype, void* stream);
+int mnb_nchw_f32_to_nhwc(const float* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MNB200_H */

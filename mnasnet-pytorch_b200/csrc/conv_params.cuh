@@ -1,0 +1,30 @@
+// Parameter block shared by the SIMT (conv_simt.cu) and tcgen05 (gemm_tc.cu) dense-convolution paths.
+#pragma once
+#include "common.cuh"
+
+namespace mnb {
+
+enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+
+struct ConvP {
+    const void* x;        // fwd/wgrad: input activations; dgrad: unused
+    const float* in_scale;
+    const float* in_shift;
+    const float* w;       // [Cout,Cin,k,k]
+    const float* bias;
+    const void* dz;       // dgrad/wgrad
+    const void* add;      // dgrad residual
+    void* out;            // fwd: z; dgrad: dx
+    float* dw;            // wgrad
+    double* stats;
+    int N, H, W, Cin, Ho, Wo, Cout, k, stride, pad;
+    int nchw_in;          // x is NCHW fp32
+    long long kchunk;     // wgrad: positions per blockIdx.z
+};
+
+// tcgen05 path (gemm_tc.cu); returns MNB_ERR_UNSUPPORTED when the shape is not covered
+int conv_fwd_tc(const ConvP& p, cudaStream_t st);
+int conv_dgrad_tc(const ConvP& p, cudaStream_t st);
+int conv_wgrad_tc(const ConvP& p, cudaStream_t st);
+
+}  // namespace mnb

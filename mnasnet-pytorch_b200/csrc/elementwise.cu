@@ -1,0 +1,677 @@
+// BatchNorm finalize / apply / backward, head (GAP, dropout, FC), loss, Adam, layout helpers.
+// All HBM-bound streaming kernels: 128-bit vector IO on NHWC rows, channel-owner threads for the
+// per-channel reductions (warp lanes run along C so every warp-level access is one contiguous segment),
+// per-CTA shared-memory partials flushed with one fp64 atomic per channel per CTA.
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mnb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// channel-owner launch geometry: blockDim = (TX, TY); thread x owns channel vector blockIdx.x*TX + x
+// ---------------------------------------------------------------------------------------------------
+struct ColGeom {
+    dim3 grid, block;
+};
+static ColGeom col_geom(long long M, int C, int ctas_per_sm = 8) {
+    int cv = C / 8;
+    int tx = largest_divisor_le(cv, 32);
+    int ty = 256 / tx;
+    long long gy = cdiv(M, ty);
+    long long cap = (long long)num_sms() * ctas_per_sm / (cv / tx);
+    if (cap < 1) cap = 1;
+    if (gy > cap) gy = cap;
+    ColGeom g;
+    g.grid = dim3(cv / tx, (unsigned)gy);
+    g.block = dim3(tx, ty);
+    return g;
+}
+
+// block-level reduction of per-thread 8-channel partials (threads sharing threadIdx.x) + fp64 atomic flush
+template <int NQ>
+__device__ __forceinline__ void flush_channel_partials(float (&acc)[NQ][8], double* out, int C, int c0) {
+    __shared__ float red[NQ][32 * 8];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nt = blockDim.x * blockDim.y;
+    for (int i = tid; i < NQ * 32 * 8; i += nt) (&red[0][0])[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&red[q][threadIdx.x * 8 + i], acc[q][i]);
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(&out[q * C + c0 + i], (double)red[q][threadIdx.x * 8 + i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BN finalize / eval coefficients
+// ---------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_k(const double* __restrict__ stats, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* running_mean, float* running_var,
+                              long long* nbt, float* scale, float* shift, float* save_mean, float* save_invstd,
+                              int C, double m, float eps, float momentum) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt) *nbt += 1;
+    if (c >= C) return;
+    double mean = stats[c] / m;
+    double var = stats[C + c] / m - mean * mean;
+    if (var < 0) var = 0;
+    double invstd = 1.0 / sqrt(var + (double)eps);
+    double s = (double)gamma[c] * invstd;
+    scale[c] = (float)s;
+    shift[c] = (float)((double)beta[c] - mean * s);
+    if (save_mean) save_mean[c] = (float)mean;
+    if (save_invstd) save_invstd[c] = (float)invstd;
+    if (running_mean) {
+        double unb = m > 1 ? var * m / (m - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
+}
+
+__global__ void bn_eval_coeffs_k(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                 float* scale, float* shift, int C, float eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = gamma[c] / sqrtf(rv[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - rm[c] * s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// y = [residual +] relu(scale*z + shift)
+// ---------------------------------------------------------------------------------------------------
+template <typename T, bool RES>
+__global__ void __launch_bounds__(256) bn_relu_apply_k(const T* __restrict__ z, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift,
+                                                       const T* __restrict__ res, T* __restrict__ y,
+                                                       long long nvec, int cv) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+         v += (long long)gridDim.x * blockDim.x) {
+        int c0 = (int)(v % cv) * 8;
+        float a[8], r[8], s[8], t[8];
+        load8(z + v * 8, a);
+        load8(scale + c0, s);
+        load8(shift + c0, t);
+        if (RES) load8(res + v * 8, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float o = fmaxf(fmaf(s[i], a[i], t[i]), 0.f);
+            a[i] = RES ? o + r[i] : o;
+        }
+        store8(y + v * 8, a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BN backward
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dA, const T* __restrict__ z,
+                                                       const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, double* sums,
+                                                       long long M, int C) {
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    float s[8], t[8], acc[2][8];
+    load8(scale + c0, s);
+    load8(shift + c0, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+    const long long stride = (long long)gridDim.y * blockDim.y;
+    long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    for (; r + stride < M; r += 2 * stride) {
+        float a0[8], z0[8], a1[8], z1[8];
+        load8(dA + r * C + c0, a0);
+        load8(z + r * C + c0, z0);
+        load8(dA + (r + stride) * C + c0, a1);
+        load8(z + (r + stride) * C + c0, z1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float g0 = fmaf(s[i], z0[i], t[i]) > 0.f ? a0[i] : 0.f;
+            float g1 = fmaf(s[i], z1[i], t[i]) > 0.f ? a1[i] : 0.f;
+            acc[0][i] += g0 + g1;
+            acc[1][i] = fmaf(g0, z0[i], fmaf(g1, z1[i], acc[1][i]));
+        }
+    }
+    for (; r < M; r += stride) {
+        float a0[8], z0[8];
+        load8(dA + r * C + c0, a0);
+        load8(z + r * C + c0, z0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float g0 = fmaf(s[i], z0[i], t[i]) > 0.f ? a0[i] : 0.f;
+            acc[0][i] += g0;
+            acc[1][i] = fmaf(g0, z0[i], acc[1][i]);
+        }
+    }
+    flush_channel_partials<2>(acc, sums, C, c0);
+}
+
+__global__ void bn_bwd_finalize_k(const double* __restrict__ sums, const float* __restrict__ scale,
+                                  const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                                  float* dgamma, float* dbeta, float* dbias, float* coef, int C, double m) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double sg = sums[c], sgz = sums[C + c];
+    double mean = save_mean[c], invstd = save_invstd[c], s = scale[c];
+    double dga = invstd * (sgz - mean * sg);
+    double a = s;
+    double b = -s * invstd * dga / m;
+    double cc = -s * sg / m - b * mean;
+    coef[c] = (float)a;
+    coef[C + c] = (float)b;
+    coef[2 * C + c] = (float)cc;
+    if (dgamma) dgamma[c] += (float)dga;
+    if (dbeta) dbeta[c] += (float)sg;
+    if (dbias) dbias[c] += (float)(a * sg + b * mean * m + cc * m);   // analytically 0 (bias cancels in BN)
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dA, const T* __restrict__ z,
+                                                      const float* __restrict__ scale,
+                                                      const float* __restrict__ shift,
+                                                      const float* __restrict__ coef, T* __restrict__ dZ,
+                                                      long long nvec, int cv) {
+    const int C = cv * 8;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+         v += (long long)gridDim.x * blockDim.x) {
+        int c0 = (int)(v % cv) * 8;
+        float a[8], zz[8], s[8], t[8], ca[8], cb[8], cc[8];
+        load8(dA + v * 8, a);
+        load8(z + v * 8, zz);
+        load8(scale + c0, s);
+        load8(shift + c0, t);
+        load8(coef + c0, ca);
+        load8(coef + C + c0, cb);
+        load8(coef + 2 * C + c0, cc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float g = fmaf(s[i], zz[i], t[i]) > 0.f ? a[i] : 0.f;
+            a[i] = fmaf(ca[i], g, fmaf(cb[i], zz[i], cc[i]));
+        }
+        store8(dZ + v * 8, a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// head
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gap_fwd_k(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                          float* __restrict__ f, int N, int HW, int cv) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * cv) return;
+    int n = idx / cv, c0 = (idx % cv) * 8;
+    const int C = cv * 8;
+    float s[8], t[8], acc[8];
+    load8(scale + c0, s);
+    load8(shift + c0, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const T* p = z + (long long)n * HW * C + c0;
+    for (int q = 0; q < HW; ++q) {
+        float a[8];
+        load8(p + (long long)q * C, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += fmaxf(fmaf(s[i], a[i], t[i]), 0.f);
+    }
+    float inv = 1.f / (float)HW;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    store8(f + (long long)n * C + c0, acc);
+}
+
+template <typename T>
+__global__ void gap_bwd_k(const float* __restrict__ df, T* __restrict__ dA, int N, int HW, int cv) {
+    long long nvec = (long long)N * HW * cv;
+    const int C = cv * 8;
+    float inv = 1.f / (float)HW;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+         v += (long long)gridDim.x * blockDim.x) {
+        int c0 = (int)(v % cv) * 8;
+        int n = (int)(v / ((long long)HW * cv));
+        float a[8];
+        load8(df + (long long)n * C + c0, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] *= inv;
+        store8(dA + v * 8, a);
+    }
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void dropout_mask_k(unsigned char* mask, long long n, float p, unsigned long long seed,
+                               unsigned long long offset, const long long* dev_step) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (dev_step) offset += (unsigned long long)(*dev_step) * (unsigned long long)n;
+    unsigned long long h = mix64(mix64(seed) ^ (offset + (unsigned long long)i));
+    float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+    mask[i] = u >= p ? 1 : 0;
+}
+
+// Small tiled SGEMM for the classifier: C[M,N] = sum_k A(m,k) * B(n,k), 64x64 tile, BK 16, 4x4 per thread.
+// The head is 0.2 % of the step's FLOPs; this keeps fp32 accuracy for the logits.
+template <class AF, class BF, class EF>
+__global__ void __launch_bounds__(256) small_gemm_k(AF af, BF bf, EF ef, int M, int N, int K) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+        for (int e = tid; e < 64 * 16; e += 256) {
+            int r, kk;
+            if (AF::k_contig) { r = e / 16; kk = e % 16; } else { r = e % 64; kk = e / 64; }
+            As[kk][r] = (m0 + r < M && k0 + kk < K) ? af(m0 + r, k0 + kk) : 0.f;
+            if (BF::k_contig) { r = e / 16; kk = e % 16; } else { r = e % 64; kk = e / 64; }
+            Bs[kk][r] = (n0 + r < N && k0 + kk < K) ? bf(n0 + r, k0 + kk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < M && n < N) ef(m, n, acc[i][j]);
+        }
+}
+
+struct XMasked {   // x[n,k]*mask*scale, k contiguous
+    static const bool k_contig = true;
+    const float* x; const unsigned char* mask; float ms; int K;
+    __device__ float operator()(int n, int k) const {
+        float v = x[(long long)n * K + k];
+        if (mask) v = mask[(long long)n * K + k] ? v * ms : 0.f;
+        return v;
+    }
+};
+struct XMaskedT {  // as B/A operand with reduction over n: element (k, n)
+    static const bool k_contig = false;
+    const float* x; const unsigned char* mask; float ms; int K;
+    __device__ float operator()(int k, int n) const {
+        float v = x[(long long)n * K + k];
+        if (mask) v = mask[(long long)n * K + k] ? v * ms : 0.f;
+        return v;
+    }
+};
+struct RowMajor {  // m[r, k] with leading dim ld, k contiguous
+    static const bool k_contig = true;
+    const float* p; int ld;
+    __device__ float operator()(int r, int k) const { return p[(long long)r * ld + k]; }
+};
+struct ColMajor {  // element (r, k) = p[k*ld + r], r contiguous
+    static const bool k_contig = false;
+    const float* p; int ld;
+    __device__ float operator()(int r, int k) const { return p[(long long)k * ld + r]; }
+};
+struct FcFwdEpi {
+    float* y; const float* b; int O; int relu;
+    __device__ void operator()(int n, int o, float v) const {
+        v += b ? b[o] : 0.f;
+        y[(long long)n * O + o] = relu ? fmaxf(v, 0.f) : v;
+    }
+};
+struct FcDgradEpi {
+    float* dx; const unsigned char* mask; float ms; const float* relu_ref; int K;
+    __device__ void operator()(int n, int k, float v) const {
+        long long i = (long long)n * K + k;
+        if (mask) v = mask[i] ? v * ms : 0.f;
+        if (relu_ref) v = relu_ref[i] > 0.f ? v : 0.f;
+        dx[i] = v;
+    }
+};
+struct AccumEpi {
+    float* dw; int ld;
+    __device__ void operator()(int o, int k, float v) const { dw[(long long)o * ld + k] += v; }
+};
+
+__global__ void colsum_accum_k(const float* __restrict__ dy, float* db, int N, int O) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= O) return;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dy[(long long)n * O + o];
+    db[o] += s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// softmax cross-entropy (mean) fused forward + backward: one CTA (128 threads) per row
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
+    for (int o = 16; o > 0; o >>= 1) {
+        float u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, u) : v + u;
+    }
+    int w = threadIdx.x / 32, l = threadIdx.x % 32;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    int nw = blockDim.x / 32;
+    v = sh[0];
+    for (int i = 1; i < nw; ++i) v = is_max ? fmaxf(v, sh[i]) : v + sh[i];
+    return v;
+}
+__global__ void __launch_bounds__(128) xent_k(const float* __restrict__ logits, const long long* __restrict__ target,
+                                              float* loss, float* dlogits, int N, int O, float gscale) {
+    __shared__ float sh[4];
+    int n = blockIdx.x;
+    const float* row = logits + (long long)n * O;
+    float mx = -INFINITY;
+    for (int o = threadIdx.x; o < O; o += blockDim.x) mx = fmaxf(mx, row[o]);
+    mx = block_reduce(mx, true, sh);
+    float se = 0.f;
+    for (int o = threadIdx.x; o < O; o += blockDim.x) se += expf(row[o] - mx);
+    se = block_reduce(se, false, sh);
+    float lse = mx + logf(se);
+    int t = (int)target[n];
+    if (threadIdx.x == 0) atomicAdd(loss, (lse - row[t]) / (float)N);
+    if (dlogits) {
+        float inv = gscale / (float)N;
+        for (int o = threadIdx.x; o < O; o += blockDim.x) {
+            float p = expf(row[o] - lse);
+            dlogits[(long long)n * O + o] = (p - (o == t ? 1.f : 0.f)) * inv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, single-tensor form) over a flat buffer
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_k(float* __restrict__ p, const float* __restrict__ g,
+                                              float* __restrict__ m, float* __restrict__ v, long long n,
+                                              float lr, float b1, float b2, float eps, int step, float gscale,
+                                              const float* dev_lr, const long long* dev_step) {
+    // torch computes the bias corrections and step size in double python floats
+    if (dev_lr) lr = *dev_lr;
+    if (dev_step) step = (int)*dev_step;
+    const double bc1 = 1.0 - pow((double)b1, (double)step);
+    const double bc2 = 1.0 - pow((double)b2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        float mi = m[i] + (1.f - b1) * (gi - m[i]);      // lerp, as torch does
+        float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= step_size * (mi / denom);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout helpers (module-boundary only; not on the fused step's path)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nhwc_to_nchw_k(const T* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
+    long long total = (long long)N * HW * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int p = (int)(i % HW);
+        int c = (int)((i / HW) % C);
+        long long n = i / ((long long)HW * C);
+        y[i] = to_f(x[(n * HW + p) * C + c]);
+    }
+}
+template <typename T>
+__global__ void nchw_to_nhwc_k(const float* __restrict__ x, T* __restrict__ y, int N, int HW, int C) {
+    long long total = (long long)N * HW * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int p = (int)((i / C) % HW);
+        long long n = i / ((long long)HW * C);
+        y[i] = from_f<T>(x[(n * C + c) * HW + p]);
+    }
+}
+
+static inline unsigned flat_grid(long long nvec, int ctas_per_sm = 8) {
+    long long b = cdiv(nvec, 256);
+    long long cap = (long long)num_sms() * ctas_per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace mnb
+
+using namespace mnb;
+
+extern "C" {
+
+int mnb_version(void) { return 100; }
+const char* mnb_last_error(void) { return g_err; }
+int mnb_device_is_sm100(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    return major == 10;
+}
+
+int mnb_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* nbt, float* scale, float* shift, float* save_mean,
+                    float* save_invstd, int C, double m, float eps, float momentum, void* stream) {
+    MNB_REQUIRE(C > 0 && m > 0, "bn_finalize: bad C/m");
+    bn_finalize_k<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, gamma, beta, running_mean, running_var,
+                                                                      nbt, scale, shift, save_mean, save_invstd, C,
+                                                                      m, eps, momentum);
+    MNB_LAUNCH_CHECK("bn_finalize");
+    return 0;
+}
+
+int mnb_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, const float* rv, float* scale,
+                       float* shift, int C, float eps, void* stream) {
+    MNB_REQUIRE(C > 0, "bn_eval_coeffs: bad C");
+    bn_eval_coeffs_k<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, rm, rv, scale, shift, C, eps);
+    MNB_LAUNCH_CHECK("bn_eval_coeffs");
+    return 0;
+}
+
+int mnb_bn_relu_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y,
+                      long long M, int C, int dtype, void* stream) {
+    MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_relu_apply: C %% 8 != 0 or M <= 0");
+    long long nvec = M * (C / 8);
+    unsigned g = flat_grid(nvec);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) {
+        if (residual) bn_relu_apply_k<float, true><<<g, 256, 0, st>>>((const float*)z, scale, shift, (const float*)residual, (float*)y, nvec, C / 8);
+        else bn_relu_apply_k<float, false><<<g, 256, 0, st>>>((const float*)z, scale, shift, nullptr, (float*)y, nvec, C / 8);
+    } else if (dtype == MNB_BF16) {
+        if (residual) bn_relu_apply_k<bf16, true><<<g, 256, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)residual, (bf16*)y, nvec, C / 8);
+        else bn_relu_apply_k<bf16, false><<<g, 256, 0, st>>>((const bf16*)z, scale, shift, nullptr, (bf16*)y, nvec, C / 8);
+    } else MNB_REQUIRE(false, "bn_relu_apply: bad dtype");
+    MNB_LAUNCH_CHECK("bn_relu_apply");
+    return 0;
+}
+
+int mnb_bn_bwd_reduce(const void* dA, const void* z, const float* scale, const float* shift, double* sums,
+                      long long M, int C, int dtype, void* stream) {
+    MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_bwd_reduce: C %% 8 != 0 or M <= 0");
+    ColGeom g = col_geom(M, C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) bn_bwd_reduce_k<float><<<g.grid, g.block, 0, st>>>((const float*)dA, (const float*)z, scale, shift, sums, M, C);
+    else if (dtype == MNB_BF16) bn_bwd_reduce_k<bf16><<<g.grid, g.block, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, sums, M, C);
+    else MNB_REQUIRE(false, "bn_bwd_reduce: bad dtype");
+    MNB_LAUNCH_CHECK("bn_bwd_reduce");
+    return 0;
+}
+
+int mnb_bn_bwd_finalize(const double* sums, const float* scale, const float* save_mean, const float* save_invstd,
+                        float* dgamma, float* dbeta, float* dbias, float* coef, int C, double m, void* stream) {
+    MNB_REQUIRE(C > 0 && m > 0, "bn_bwd_finalize: bad C/m");
+    bn_bwd_finalize_k<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, scale, save_mean, save_invstd, dgamma,
+                                                                          dbeta, dbias, coef, C, m);
+    MNB_LAUNCH_CHECK("bn_bwd_finalize");
+    return 0;
+}
+
+int mnb_bn_bwd_apply(const void* dA, const void* z, const float* scale, const float* shift, const float* coef,
+                     void* dZ, long long M, int C, int dtype, void* stream) {
+    MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_bwd_apply: C %% 8 != 0 or M <= 0");
+    long long nvec = M * (C / 8);
+    unsigned g = flat_grid(nvec);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) bn_bwd_apply_k<float><<<g, 256, 0, st>>>((const float*)dA, (const float*)z, scale, shift, coef, (float*)dZ, nvec, C / 8);
+    else if (dtype == MNB_BF16) bn_bwd_apply_k<bf16><<<g, 256, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, coef, (bf16*)dZ, nvec, C / 8);
+    else MNB_REQUIRE(false, "bn_bwd_apply: bad dtype");
+    MNB_LAUNCH_CHECK("bn_bwd_apply");
+    return 0;
+}
+
+int mnb_gap_fwd(const void* z, const float* scale, const float* shift, float* f, int N, int HW, int C, int dtype,
+                void* stream) {
+    MNB_REQUIRE(C % 8 == 0 && N > 0 && HW > 0, "gap_fwd: bad shape");
+    int total = N * (C / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) gap_fwd_k<float><<<(total + 127) / 128, 128, 0, st>>>((const float*)z, scale, shift, f, N, HW, C / 8);
+    else if (dtype == MNB_BF16) gap_fwd_k<bf16><<<(total + 127) / 128, 128, 0, st>>>((const bf16*)z, scale, shift, f, N, HW, C / 8);
+    else MNB_REQUIRE(false, "gap_fwd: bad dtype");
+    MNB_LAUNCH_CHECK("gap_fwd");
+    return 0;
+}
+
+int mnb_gap_bwd(const float* df, void* dA, int N, int HW, int C, int dtype, void* stream) {
+    MNB_REQUIRE(C % 8 == 0 && N > 0 && HW > 0, "gap_bwd: bad shape");
+    long long nvec = (long long)N * HW * (C / 8);
+    unsigned g = flat_grid(nvec);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) gap_bwd_k<float><<<g, 256, 0, st>>>(df, (float*)dA, N, HW, C / 8);
+    else if (dtype == MNB_BF16) gap_bwd_k<bf16><<<g, 256, 0, st>>>(df, (bf16*)dA, N, HW, C / 8);
+    else MNB_REQUIRE(false, "gap_bwd: bad dtype");
+    MNB_LAUNCH_CHECK("gap_bwd");
+    return 0;
+}
+
+int mnb_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned long long offset,
+                     const long long* dev_step, void* stream) {
+    MNB_REQUIRE(n > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad n/p");
+    dropout_mask_k<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed, offset, dev_step);
+    MNB_LAUNCH_CHECK("dropout_mask");
+    return 0;
+}
+
+int mnb_fc_fwd(const float* x, const unsigned char* mask, float mask_scale, const float* w, const float* b, float* y,
+               int relu_out, int N, int K, int O, void* stream) {
+    MNB_REQUIRE(N > 0 && K > 0 && O > 0, "fc_fwd: bad shape");
+    XMasked af{x, mask, mask_scale, K};
+    RowMajor bf_{w, K};
+    FcFwdEpi ef{y, b, O, relu_out};
+    dim3 grid((O + 63) / 64, (N + 63) / 64);
+    small_gemm_k<<<grid, 256, 0, (cudaStream_t)stream>>>(af, bf_, ef, N, O, K);
+    MNB_LAUNCH_CHECK("fc_fwd");
+    return 0;
+}
+
+int mnb_fc_dgrad(const float* dy, const float* w, const unsigned char* mask, float mask_scale, const float* relu_ref,
+                 float* dx, int N, int K, int O, void* stream) {
+    MNB_REQUIRE(N > 0 && K > 0 && O > 0, "fc_dgrad: bad shape");
+    RowMajor af{dy, O};        // A(n, o)
+    ColMajor bf_{w, K};        // B(k, o) = w[o*K + k]
+    FcDgradEpi ef{dx, mask, mask_scale, relu_ref, K};
+    dim3 grid((K + 63) / 64, (N + 63) / 64);
+    small_gemm_k<<<grid, 256, 0, (cudaStream_t)stream>>>(af, bf_, ef, N, K, O);
+    MNB_LAUNCH_CHECK("fc_dgrad");
+    return 0;
+}
+
+int mnb_fc_wgrad(const float* x, const unsigned char* mask, float mask_scale, const float* dy, float* dw, float* db,
+                 int N, int K, int O, void* stream) {
+    MNB_REQUIRE(N > 0 && K > 0 && O > 0, "fc_wgrad: bad shape");
+    ColMajor af{dy, O};                      // A(o, n) = dy[n*O + o]
+    XMaskedT bf_{x, mask, mask_scale, K};    // B(k, n) = xm[n*K + k]
+    AccumEpi ef{dw, K};
+    dim3 grid((K + 63) / 64, (O + 63) / 64);
+    small_gemm_k<<<grid, 256, 0, (cudaStream_t)stream>>>(af, bf_, ef, O, K, N);
+    MNB_LAUNCH_CHECK("fc_wgrad");
+    if (db) {
+        colsum_accum_k<<<(O + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dy, db, N, O);
+        MNB_LAUNCH_CHECK("fc_wgrad(bias)");
+    }
+    return 0;
+}
+
+int mnb_xent_fwd_bwd(const float* logits, const long long* target, float* loss, float* dlogits, int N, int O,
+                     float grad_scale, void* stream) {
+    MNB_REQUIRE(N > 0 && O > 0, "xent: bad shape");
+    xent_k<<<N, 128, 0, (cudaStream_t)stream>>>(logits, target, loss, dlogits, N, O, grad_scale);
+    MNB_LAUNCH_CHECK("xent");
+    return 0;
+}
+
+int mnb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, int step, float grad_scale, const float* dev_lr, const long long* dev_step,
+                  void* stream) {
+    MNB_REQUIRE(n > 0 && (step >= 1 || dev_step), "adam: bad n/step");
+    adam_k<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale,
+                                                           dev_lr, dev_step);
+    MNB_LAUNCH_CHECK("adam");
+    return 0;
+}
+
+__global__ void counter_inc_k(long long* c) { *c += 1; }
+int mnb_counter_inc(long long* counter, void* stream) {
+    counter_inc_k<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+    MNB_LAUNCH_CHECK("counter_inc");
+    return 0;
+}
+
+int mnb_nhwc_to_nchw_f32(const void* x, float* y, int N, int H, int W, int C, int dtype, void* stream) {
+    long long total = (long long)N * H * W * C;
+    MNB_REQUIRE(total > 0, "nhwc_to_nchw: empty");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) nhwc_to_nchw_k<float><<<flat_grid(total), 256, 0, st>>>((const float*)x, y, N, H * W, C);
+    else if (dtype == MNB_BF16) nhwc_to_nchw_k<bf16><<<flat_grid(total), 256, 0, st>>>((const bf16*)x, y, N, H * W, C);
+    else MNB_REQUIRE(false, "nhwc_to_nchw: bad dtype");
+    MNB_LAUNCH_CHECK("nhwc_to_nchw");
+    return 0;
+}
+
+int mnb_nchw_f32_to_nhwc(const float* x, void* y, int N, int H, int W, int C, int dtype, void* stream) {
+    long long total = (long long)N * H * W * C;
+    MNB_REQUIRE(total > 0, "nchw_to_nhwc: empty");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) nchw_to_nhwc_k<float><<<flat_grid(total), 256, 0, st>>>(x, (float*)y, N, H * W, C);
+    else if (dtype == MNB_BF16) nchw_to_nhwc_k<bf16><<<flat_grid(total), 256, 0, st>>>(x, (bf16*)y, N, H * W, C);
+    else MNB_REQUIRE(false, "nchw_to_nhwc: bad dtype");
+    MNB_LAUNCH_CHECK("nchw_to_nhwc");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,768 @@
+"""Lowering of the reference's module tree to a static program of libmnb200 kernel launches.
+
+Host side of the drop-in boundary: the reference drives the hot path with six lines
+(src/train.py:433-440: ``out = model(input); loss = criterion(out, target); optimizer.zero_grad();
+loss.backward(); optimizer.step()``).  ``run_module`` makes ``model(input)`` / ``loss.backward()`` work
+unchanged through ``torch.autograd.Function``; ``Engine.train_step`` is the fused variant (loss, backward and
+Adam also in our kernels, optional NCCL gradient all-reduce, optional CUDA-graph replay).
+
+Data layout in HBM: activations NHWC (bf16 or fp32).  For every ConvBlock *application* the
+program keeps the raw conv output Z plus per-channel (scale, shift, mean, invstd); A = relu(scale*Z+shift)
+is never stored -- consumers recompute it on load.  Residual-block inputs/outputs (narrow tensors) are
+materialised once.  Parameters / gradients / Adam moments live in flat fp32 buffers ordered
+backward-ready-first so NCCL buckets are contiguous slices; nn.Parameters are views into them.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, check
+
+DTYPES = {"fp32": (_lib.MNB_F32, torch.float32), "bf16": (_lib.MNB_BF16, torch.bfloat16)}
+IMPLS = {"auto": 0, "simt": 1, "tc": 2}
+BN_EPS_DEFAULT = 1e-5
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mnb200: a CUDA device (B200, sm_100a) is required; there is no CPU fallback")
+
+
+class Ref:
+    """An activation in HBM: tensor t viewed as [N,H,W,C]; if scale is set the VALUE is relu(scale*t+shift)."""
+    __slots__ = ("t", "N", "H", "W", "C", "scale", "shift", "nchw")
+
+    def __init__(self, t, N, H, W, C, scale=None, shift=None, nchw=False):
+        self.t, self.N, self.H, self.W, self.C = t, N, H, W, C
+        self.scale, self.shift, self.nchw = scale, shift, nchw
+
+    @property
+    def M(self):
+        return self.N * self.H * self.W
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient buffers (+ flat BN buffers).  Order: reverse of registration order,
+    i.e. the order in which gradients become ready in backward (classifier first, stem last)."""
+    ALIGN = 8
+
+    def __init__(self, module: nn.Module, device):
+        self.device = device
+        seen, params = set(), []
+        for name, p in module.named_parameters():          # de-duplicated by torch (shared blocks once)
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append((name, p))
+        params = params[::-1]
+        self.names = [n for n, _ in params]
+        self.params = [p for _, p in params]
+        off, self.offsets = 0, {}
+        for p in self.params:
+            self.offsets[id(p)] = (off, p.numel())
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.total = off
+        self.flat = torch.zeros(off, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(off, device=device, dtype=torch.float32)
+        for p in self.params:
+            o, n = self.offsets[id(p)]
+            v = self.flat[o:o + n].view(p.shape)
+            v.copy_(p.data.to(device=device, dtype=torch.float32))
+            p.data = v
+        # BN buffers
+        fb, ib, seenb = [], [], set()
+        for name, b in module.named_buffers():
+            if id(b) in seenb:
+                continue
+            seenb.add(id(b))
+            (ib if b.dtype == torch.long else fb).append(b)
+        self.fbuf = torch.zeros(max(1, sum(b.numel() for b in fb)), device=device, dtype=torch.float32)
+        self.ibuf = torch.zeros(max(1, sum(b.numel() for b in ib)), device=device, dtype=torch.long)
+        self._fb, self._ib = fb, ib
+        o = 0
+        for b in fb:
+            v = self.fbuf[o:o + b.numel()].view(b.shape)
+            v.copy_(b.data.to(device))
+            b.data = v
+            o += b.numel()
+        o = 0
+        for b in ib:
+            v = self.ibuf[o:o + b.numel()].view(b.shape)
+            v.copy_(b.data.to(device))
+            b.data = v
+            o += b.numel()
+        self.m = None
+        self.v = None
+
+    def valid(self):
+        for p in (self.params[0], self.params[-1]):
+            o, _ = self.offsets[id(p)]
+            if p.data_ptr() != self.flat.data_ptr() + 4 * o:
+                return False
+        for lst, buf in ((self._fb, self.fbuf), (self._ib, self.ibuf)):
+            if lst and lst[0].data_ptr() != buf.data_ptr():
+                return False
+        return True
+
+    def gptr(self, p):
+        return self.grad.data_ptr() + 4 * self.offsets[id(p)][0]
+
+    def grad_views(self, src=None):
+        src = self.grad if src is None else src
+        out = {}
+        for p in self.params:
+            o, n = self.offsets[id(p)]
+            out[id(p)] = src[o:o + n].view(p.shape)
+        return out
+
+    def adam_state(self):
+        if self.m is None:
+            self.m = torch.zeros_like(self.flat)
+            self.v = torch.zeros_like(self.flat)
+        return self.m, self.v
+
+    def buckets(self):
+        """Contiguous slices of the flat gradient buffer in backward-ready order, cut at top-level-stage
+        boundaries: classifier+features.7 | features.6+features.5 | rest."""
+        groups = [("classifier", "features.7"), ("features.6", "features.5")]
+
+        def gidx(name):
+            parts = name.split(".")
+            s_ = parts[0] if parts[0] != "features" else "features." + parts[1]
+            for i, g in enumerate(groups):
+                if s_ in g:
+                    return i
+            return len(groups)
+        edges, prev = [0], None
+        for name, p in zip(self.names, self.params):
+            g = gidx(name)
+            if prev is not None and g != prev:
+                edges.append(self.offsets[id(p)][0])
+            prev = g
+        edges.append(self.total)
+        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1) if edges[i + 1] > edges[i]]
+
+
+class _ConvApp:
+    """One application of a ConvBlock inside a plan."""
+    __slots__ = ("cb", "inp", "z", "stats", "sums", "scale", "shift", "mean", "invstd", "coef", "kind",
+                 "Ho", "Wo", "Cout", "k", "stride", "pad", "need_dgrad", "m")
+
+
+class Plan:
+    """Static program for one input shape (N,H,W): buffers + forward/backward op lists."""
+
+    def __init__(self, eng: "Engine", N: int, H: int, W: int):
+        self.eng, self.N, self.H, self.W = eng, N, H, W
+        self.dev = eng.device
+        self.code, self.tdtype = DTYPES[eng.dtype]
+        self.keep = []              # tensors owned by the plan
+        self.fwd, self.fwd_eval, self.bwd = [], [], []
+        self.apps: List[_ConvApp] = []
+        self.tape = []
+        self.generation = 0
+        self.last_write = {}
+        self._arena_f, self._arena_d = [], []   # (numel) requests
+        self._build()
+
+    # ---- allocation helpers ---------------------------------------------------------------------
+    def _act(self, N, H, W, C):
+        t = torch.empty((N, H, W, C), device=self.dev, dtype=self.tdtype)
+        self.keep.append(t)
+        return t
+
+    def _f32(self, *shape):
+        t = torch.zeros(shape, device=self.dev, dtype=torch.float32)
+        self.keep.append(t)
+        return t
+
+    # ---- program construction --------------------------------------------------------------------
+    def _build(self):
+        eng = self.eng
+        mod = eng.module
+        N, H, W = self.N, self.H, self.W
+        # fp64 arena for BN statistics (fwd stats + bwd sums), zeroed once per step
+        self._dstat_chunks = []
+        kind = getattr(mod, "_mnb", None)
+        if kind == "net":
+            ref = Ref(None, N, H, W, 3, nchw=True)
+            ref = self._emit(mod.features, ref)
+            self._emit_head(mod, ref)
+        else:
+            cin = eng.in_channels
+            # standalone sub-module: convert the NCHW fp32 input to NHWC once, run, convert back
+            xin = self._act(N, H, W, cin)
+            self.sub_in = xin
+            ref = Ref(xin, N, H, W, cin)
+            out = self._emit(mod, ref)
+            out = self._materialize(out)
+            self.sub_out = out
+            self.out_nchw = torch.empty((N, out.C, out.H, out.W), device=self.dev, dtype=torch.float32)
+            self.keep.append(self.out_nchw)
+        # allocate the fp64 arena
+        total = sum(n for n, _ in self._dstat_chunks)
+        self.dstats = torch.zeros(max(total, 1), device=self.dev, dtype=torch.float64)
+        self._dstat_base = self.dstats.data_ptr()
+        self._emit_backward()
+
+    def _dstat(self, n):
+        """Reserve n doubles in the arena; returns a lazy pointer (resolved after allocation)."""
+        off = sum(c for c, _ in self._dstat_chunks)
+        h = _Lazy(self, off * 8)
+        self._dstat_chunks.append((n, h))
+        return h
+
+    def _emit(self, mod, ref: Ref) -> Ref:
+        kind = getattr(mod, "_mnb", None)
+        if kind == "convblock":
+            return self._emit_convblock(mod, ref)
+        if kind == "chain":
+            for child in mod.sequence:
+                ref = self._emit(child, ref)
+            return ref
+        if kind == "resblock":
+            x = self._materialize(ref)
+            self.tape.append(("res_begin", x))
+            r = x
+            for child in mod.sequence:
+                r = self._emit(child, r)
+            y = self._act(x.N, x.H, x.W, x.C)
+            M = x.M
+            self._op(self.fwd, "mnb_bn_relu_apply", r.t, r.scale, r.shift, x.t, y, M, x.C, self.code)
+            self._op(self.fwd_eval, "mnb_bn_relu_apply", r.t, r.scale, r.shift, x.t, y, M, x.C, self.code)
+            self.tape.append(("res_end", x))
+            return Ref(y, x.N, x.H, x.W, x.C)
+        if isinstance(mod, nn.Sequential):
+            for child in mod:
+                ref = self._emit(child, ref)
+            return ref
+        raise TypeError(f"mnb200 cannot lower module of type {type(mod).__name__}")
+
+    def _materialize(self, ref: Ref) -> Ref:
+        if ref.scale is None and not ref.nchw:
+            return ref
+        if ref.nchw:
+            raise RuntimeError("NCHW input can only feed a dense ConvBlock")
+        y = self._act(ref.N, ref.H, ref.W, ref.C)
+        for ops in (self.fwd, self.fwd_eval):
+            self._op(ops, "mnb_bn_relu_apply", ref.t, ref.scale, ref.shift, None, y, ref.M, ref.C, self.code)
+        self.tape.append(("materialize", ref))
+        return Ref(y, ref.N, ref.H, ref.W, ref.C)
+
+    def _emit_convblock(self, cb, ref: Ref) -> Ref:
+        conv, bn = cb.conv, cb.bn
+        k, stride, pad, groups = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.groups
+        cin, cout = conv.in_channels, conv.out_channels
+        if cin != ref.C:
+            raise ValueError(f"channel mismatch: ConvBlock expects {cin}, got {ref.C}")
+        Ho = (ref.H + 2 * pad - k) // stride + 1
+        Wo = (ref.W + 2 * pad - k) // stride + 1
+        a = _ConvApp()
+        a.cb, a.inp, a.Ho, a.Wo, a.Cout, a.k, a.stride, a.pad = cb, ref, Ho, Wo, cout, k, stride, pad
+        a.kind = "dw" if groups > 1 else "dense"
+        if a.kind == "dw" and (groups != cin or cin != cout or stride != 1 or pad != k // 2):
+            raise ValueError("only depthwise stride-1 'same' grouped convs are lowered")
+        a.z = self._act(ref.N, Ho, Wo, cout)
+        a.m = float(ref.N * Ho * Wo)
+        a.stats = self._dstat(2 * cout)
+        a.sums = self._dstat(2 * cout)
+        vec = self._f32(4, cout)
+        a.scale, a.shift, a.mean, a.invstd = vec[0], vec[1], vec[2], vec[3]
+        a.coef = self._f32(3, cout)
+        a.need_dgrad = not ref.nchw        # the stem reads the network input: no data gradient
+        eng = self.eng
+        x_t = ref.t if not ref.nchw else _InputPtr(self)
+        layout = _lib.LAYOUT_NCHW_F32 if ref.nchw else _lib.LAYOUT_NHWC
+        for ops, train in ((self.fwd, True), (self.fwd_eval, False)):
+            st = a.stats if train else None
+            if a.kind == "dense":
+                self._op(ops, "mnb_conv_fwd", x_t, ref.scale, ref.shift, conv.weight, conv.bias, a.z, st,
+                         ref.N, ref.H, ref.W, cin, cout, k, stride, pad, self.code, layout, eng.impl)
+            else:
+                self._op(ops, "mnb_dw_fwd", x_t, ref.scale, ref.shift, conv.weight, conv.bias, a.z, st,
+                         ref.N, ref.H, ref.W, cin, k, self.code)
+            if train:
+                self._op(ops, "mnb_bn_finalize", a.stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                         bn.num_batches_tracked, a.scale, a.shift, a.mean, a.invstd, cout, a.m,
+                         float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1))
+            else:
+                self._op(ops, "mnb_bn_eval_coeffs", bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                         a.scale, a.shift, cout, float(bn.eps))
+        self.apps.append(a)
+        self.tape.append(("conv", a))
+        return Ref(a.z, ref.N, Ho, Wo, cout, a.scale, a.shift)
+
+    def _emit_head(self, mod, ref: Ref):
+        """AdaptiveAvgPool2d(1) + classifier Sequential of Dropout / Linear / ReLU (classifiers.py:56-111)."""
+        N, C = ref.N, ref.C
+        self.head_in = ref
+        self.f = self._f32(N, C)
+        for ops in (self.fwd, self.fwd_eval):
+            self._op(ops, "mnb_gap_fwd", ref.t, ref.scale, ref.shift, self.f, N, ref.H * ref.W, C, self.code)
+        children = list(mod.classifier)
+        cur, width, pending = self.f, C, None
+        self.head = []
+        self.dropout_masks = []
+        di = 0
+        for i, ch in enumerate(children):
+            if isinstance(ch, nn.Dropout):
+                mask = torch.ones((N, width), device=self.dev, dtype=torch.uint8)
+                self.keep.append(mask)
+                self.dropout_masks.append((mask, float(ch.p)))
+                pending = (mask, float(ch.p), di)
+                di += 1
+            elif isinstance(ch, nn.Linear):
+                relu = i + 1 < len(children) and isinstance(children[i + 1], nn.ReLU)
+                y = self._f32(N, ch.out_features)
+                rec = {"x": cur, "mask": None, "ms": 1.0, "lin": ch, "y": y, "relu": relu, "K": width,
+                       "O": ch.out_features}
+                if pending is not None and pending[1] > 0:
+                    mask, p, idx = pending
+                    rec.update(mask=mask, ms=1.0 / (1.0 - p), p=p, idx=idx)
+                    self.fwd.append(_DropoutOp(self, mask, N * width, p, idx))
+                    self._op(self.fwd, "mnb_fc_fwd", cur, _MaskPtr(self, mask), _MaskScale(self, rec["ms"]),
+                             ch.weight, ch.bias, y, int(relu), N, width, ch.out_features)
+                else:
+                    self._op(self.fwd, "mnb_fc_fwd", cur, None, 1.0, ch.weight, ch.bias, y, int(relu), N, width,
+                             ch.out_features)
+                self._op(self.fwd_eval, "mnb_fc_fwd", cur, None, 1.0, ch.weight, ch.bias, y, int(relu), N,
+                         width, ch.out_features)
+                self.head.append(rec)
+                cur, width, pending = y, ch.out_features, None
+            elif isinstance(ch, nn.ReLU):
+                pass
+            else:
+                raise TypeError(f"classifier child {type(ch).__name__} not lowered")
+        self.logits = cur
+        self.num_out = width
+        self.dlogits = self._f32(N, width)
+        self.loss = self._f32(1)
+        self.target = torch.zeros(N, device=self.dev, dtype=torch.long)
+
+    # ---- backward program ----------------------------------------------------------------------------
+    def _emit_backward(self):
+        eng = self.eng
+        maxel = 1
+        for a in self.apps:
+            maxel = max(maxel, a.inp.M * a.inp.C if not a.inp.nchw else 1, int(a.m) * a.Cout)
+        pool = [torch.empty(maxel, device=self.dev, dtype=self.tdtype) for _ in range(4)]
+        self.keep += pool
+        free = list(pool)
+        ops = self.bwd
+        net = getattr(eng.module, "_mnb", None) == "net"
+        if net:
+            # head backward
+            g = self.dlogits
+            for i in range(len(self.head) - 1, -1, -1):
+                r = self.head[i]
+                lin = r["lin"]
+                maskp = _MaskPtr(self, r["mask"]) if r["mask"] is not None else None
+                ms = _MaskScale(self, r["ms"]) if r["mask"] is not None else 1.0
+                self._op(ops, "mnb_fc_wgrad", r["x"], maskp, ms, g, _G(lin.weight), _G(lin.bias), self.N, r["K"],
+                         r["O"])
+                dx = self._f32(self.N, r["K"])
+                relu_ref = r["x"] if (i > 0 and self.head[i - 1]["relu"]) else None
+                self._op(ops, "mnb_fc_dgrad", g, lin.weight, maskp, ms, relu_ref, dx, self.N, r["K"], r["O"])
+                g = dx
+            gbuf = free.pop()
+            hi = self.head_in
+            self._op(ops, "mnb_gap_bwd", g, gbuf, self.N, hi.H * hi.W, hi.C, self.code)
+        else:
+            gbuf = free.pop()
+            self.sub_dout = gbuf          # filled from the NCHW grad_output at run time
+        held = []                          # stack of residual-skip gradients
+        for idx in range(len(self.tape) - 1, -1, -1):
+            entry = self.tape[idx]
+            tag = entry[0]
+            if tag == "res_end":
+                held.append(gbuf)          # dY of the block: feeds CB3 as dA and the skip add of CB1's dgrad
+            elif tag == "res_begin":
+                skip = held.pop()
+                if skip is not gbuf:
+                    free.append(skip)
+            elif tag == "materialize":
+                pass                       # dY == dA of the producing conv
+            elif tag == "conv":
+                a = entry[1]
+                conv, bn = a.cb.conv, a.cb.bn
+                M, C = int(a.m), a.Cout
+                dz = free.pop()
+                self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code)
+                self._op(ops, "mnb_bn_bwd_finalize", a.sums, a.scale, a.mean, a.invstd, _G(bn.weight),
+                         _G(bn.bias), _G(conv.bias), a.coef, C, a.m)
+                self._op(ops, "mnb_bn_bwd_apply", gbuf, a.z, a.scale, a.shift, a.coef, dz, M, C, self.code)
+                in_held = any(gbuf is h for h in held)
+                if not in_held:
+                    free.append(gbuf)
+                r = a.inp
+                x_t = r.t if not r.nchw else _InputPtr(self)
+                layout = _lib.LAYOUT_NCHW_F32 if r.nchw else _lib.LAYOUT_NHWC
+                if a.kind == "dense":
+                    self._op(ops, "mnb_conv_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W,
+                             r.C, C, a.k, a.stride, a.pad, self.code, layout, eng.impl)
+                else:
+                    self._op(ops, "mnb_dw_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W, r.C,
+                             a.k, self.code)
+                if a.need_dgrad:
+                    dx = free.pop()
+                    # the first conv of a residual block adds the skip gradient (dY) into its dgrad output
+                    add = None
+                    if idx > 0 and self.tape[idx - 1][0] == "res_begin":
+                        add = held[-1]
+                    if a.kind == "dense":
+                        self._op(ops, "mnb_conv_dgrad", dz, conv.weight, add, dx, r.N, r.H, r.W, r.C, C, a.k,
+                                 a.stride, a.pad, self.code, eng.impl)
+                    else:
+                        self._op(ops, "mnb_dw_dgrad", dz, conv.weight, dx, r.N, r.H, r.W, r.C, a.k, self.code)
+                    free.append(dz)
+                    gbuf = dx
+                else:
+                    free.append(dz)
+                    gbuf = None
+        self.sub_din = gbuf
+
+    # ---- op plumbing -----------------------------------------------------------------------------------
+    def _op(self, ops, name, *args):
+        fn = getattr(lib, name)
+        conv = []
+        if ops is self.bwd:
+            for a in args:
+                if isinstance(a, _G):
+                    self.last_write[id(a.p)] = len(ops) + 1     # gradient slot final after this op index
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                conv.append(_TensorPtr(a))
+            elif isinstance(a, nn.Parameter):
+                conv.append(_TensorPtr(a))
+            else:
+                conv.append(a)
+        ops.append(_Op(name, fn, conv, self))
+
+    def run(self, ops, stream):
+        for op in ops:
+            op(stream)
+
+
+class _TensorPtr:
+    """Pointer of a tensor resolved at bind time (plan buffers, and parameters/buffers which are views into
+    the engine's flat stores -- validity is checked once per call by ParamStore.valid())."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+    def resolve(self, plan):
+        return self.t.data_ptr()
+
+
+class _G:
+    """Pointer of the gradient slot of a parameter in the flat gradient buffer."""
+    __slots__ = ("p",)
+
+    def __init__(self, p):
+        self.p = p
+
+    def resolve(self, plan):
+        return plan.eng.store.gptr(self.p)
+
+
+class _Lazy:
+    __slots__ = ("plan", "off")
+
+    def __init__(self, plan, off):
+        self.plan, self.off = plan, off
+
+    def resolve(self, plan):
+        return plan._dstat_base + self.off
+
+
+class _InputPtr:
+    """The NCHW fp32 network input: bound per call."""
+    __slots__ = ("plan",)
+
+    def __init__(self, plan):
+        self.plan = plan
+
+    def resolve(self, plan):
+        return None        # dynamic
+
+
+class _MaskPtr:
+    """Dropout mask pointer, NULL when dropout is disabled for this call."""
+    __slots__ = ("plan", "mask")
+
+    def __init__(self, plan, mask):
+        self.plan, self.mask = plan, mask
+
+    def resolve(self, plan):
+        return None        # dynamic
+
+
+class _MaskScale:
+    __slots__ = ("plan", "ms")
+
+    def __init__(self, plan, ms):
+        self.plan, self.ms = plan, ms
+
+    def resolve(self, plan):
+        return None        # dynamic
+
+
+class _Op:
+    """A bound kernel launch.  Static arguments are resolved once (first run after (re)binding); dynamic
+    ones (network input pointer, dropout on/off) are patched per call."""
+
+    def __init__(self, name, fn, args, plan):
+        self.name, self.fn, self.args, self.plan = name, fn, args, plan
+        self.bound = None
+        self.dyn = [(i, a) for i, a in enumerate(args) if isinstance(a, (_InputPtr, _MaskPtr, _MaskScale))]
+
+    def bind(self):
+        plan = self.plan
+        self.bound = [a.resolve(plan) if hasattr(a, "resolve") else a for a in self.args]
+
+    def __call__(self, stream):
+        if self.bound is None:
+            self.bind()
+        b = self.bound
+        plan = self.plan
+        for i, a in self.dyn:
+            if isinstance(a, _InputPtr):
+                b[i] = plan.cur_input_ptr
+            elif isinstance(a, _MaskPtr):
+                b[i] = a.mask.data_ptr() if plan.dropout_active else None
+            else:
+                b[i] = a.ms if plan.dropout_active else 1.0
+        rc = self.fn(*b, stream)
+        if rc != 0:
+            check(rc, self.name)
+
+
+class _DropoutOp:
+    """Generates a dropout keep-mask unless dropout is off or masks were injected for this call."""
+
+    def __init__(self, plan, mask, n, p, idx):
+        self.plan, self.mask, self.n, self.p, self.idx = plan, mask, n, p, idx
+        self.name = "mnb_dropout_mask"
+
+    def __call__(self, stream):
+        plan = self.plan
+        if not plan.dropout_active or plan.masks_injected:
+            return
+        eng = plan.eng
+        check(lib.mnb_dropout_mask(self.mask.data_ptr(), self.n, self.p, eng.seed,
+                                   (self.idx + 1) << 40, eng.dev_step.data_ptr(), stream), self.name)
+
+
+class Engine:
+    """Owns the flat parameter store and the per-shape plans of one lowered module."""
+
+    def __init__(self, module: nn.Module, dtype: str = "bf16", impl: str = "auto", device=None, seed: int = 0):
+        _require_cuda()
+        if dtype not in DTYPES:
+            raise ValueError(f"dtype must be one of {list(DTYPES)}")
+        self.module = module
+        self.dtype, self.impl = dtype, IMPLS[impl]
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.in_channels = _first_conv(module).in_channels
+        self.store = ParamStore(module, self.device)
+        self.plans = {}
+        self.seed = int(seed)
+        self.dev_step = torch.zeros(1, device=self.device, dtype=torch.long)   # optimizer / RNG step counter
+        self.dev_lr = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self.host_step = 0
+        self.dropout = "on"            # "on" | "off"
+        self.grad_hook = None          # DDP: callable(engine, stage) invoked while backward is enqueued
+        self.graphs = {}
+
+    def plan(self, N, H, W) -> Plan:
+        key = (N, H, W)
+        p = self.plans.get(key)
+        if p is None:
+            p = Plan(self, N, H, W)
+            self.plans[key] = p
+        return p
+
+    def _check_store(self):
+        if not self.store.valid():
+            # parameters were re-allocated (e.g. model.to()/load on another device): rebuild everything
+            self.store = ParamStore(self.module, self.device)
+            self.plans.clear()
+            self.graphs.clear()
+        return self.store
+
+    # ---- forward / backward on the current stream ------------------------------------------------
+    def forward(self, x: torch.Tensor, train: bool, dropout_masks=None) -> Plan:
+        self._check_store()
+        if x.dim() != 4:
+            raise ValueError("expected N x C x H x W input")
+        if not x.is_cuda:
+            raise RuntimeError("mnb200: input must be a CUDA tensor (no CPU fallback)")
+        x = x.contiguous().float()
+        N, C, H, W = x.shape
+        plan = self.plan(N, H, W)
+        stream = torch.cuda.current_stream().cuda_stream
+        plan.cur_input = x
+        plan.cur_input_ptr = x.data_ptr()
+        drop_on = self.dropout == "on" and any(isinstance(m, nn.Dropout) and m.training
+                                               for m in self.module.modules())
+        plan.dropout_active = bool(train) and (drop_on or dropout_masks is not None)
+        plan.masks_injected = dropout_masks is not None
+        if dropout_masks is not None:
+            for (mask, _), src in zip(plan.dropout_masks, dropout_masks):
+                mask.copy_(src.to(device=self.device, dtype=torch.uint8))
+        sub = getattr(self.module, "_mnb", None) != "net"
+        if sub:
+            check(lib.mnb_nchw_f32_to_nhwc(x.data_ptr(), plan.sub_in.data_ptr(), N, H, W, C, plan.code, stream),
+                  "nchw_to_nhwc")
+        if train:
+            plan.dstats.zero_()
+            plan.run(plan.fwd, stream)
+        else:
+            plan.run(plan.fwd_eval, stream)
+        if sub:
+            o = plan.sub_out
+            check(lib.mnb_nhwc_to_nchw_f32(o.t.data_ptr(), plan.out_nchw.data_ptr(), o.N, o.H, o.W, o.C, plan.code,
+                                           stream), "nhwc_to_nchw")
+        plan.generation += 1
+        return plan
+
+    def backward(self, plan: Plan, zero_grads: bool = True):
+        """Runs the backward program; dlogits (or sub_dout) must already be in place."""
+        stream = torch.cuda.current_stream().cuda_stream
+        if zero_grads:
+            self.store.grad.zero_()
+        hook = self.grad_hook
+        if hook is None:
+            plan.run(plan.bwd, stream)
+        else:
+            hook.run_backward(self, plan, stream)
+
+    # ---- fused training step (train.py:433-440 entirely in libmnb200) -----------------------------
+    def train_step(self, x, target, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, allreduce=None, world_size=1):
+        """forward + CrossEntropyLoss(mean) + backward + Adam.  Returns the (device) loss tensor of shape [1].
+        `allreduce`: optional callable(engine) that averages self.store.grad across ranks (mnb200.ddp)."""
+        plan = self.forward(x, True)
+        stream = torch.cuda.current_stream().cuda_stream
+        plan.target.copy_(target, non_blocking=True)
+        plan.loss.zero_()
+        check(lib.mnb_xent_fwd_bwd(plan.logits.data_ptr(), plan.target.data_ptr(), plan.loss.data_ptr(),
+                                   plan.dlogits.data_ptr(), plan.N, plan.num_out, 1.0, stream), "xent")
+        self.backward(plan)
+        gscale = 1.0
+        if allreduce is not None:
+            allreduce(self)
+            gscale = 1.0 / world_size
+        self.adam(lr, betas, eps, gscale)
+        return plan.loss
+
+    def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        stream = torch.cuda.current_stream().cuda_stream
+        m, v = self.store.adam_state()
+        self.host_step += 1
+        check(lib.mnb_counter_inc(self.dev_step.data_ptr(), stream), "counter_inc")
+        st = self.store
+        check(lib.mnb_adam_step(st.flat.data_ptr(), st.grad.data_ptr(), m.data_ptr(), v.data_ptr(), st.total,
+                                float(lr), betas[0], betas[1], eps, self.host_step, grad_scale, None,
+                                self.dev_step.data_ptr(), stream), "adam")
+
+    def logits(self, plan):
+        return plan.logits
+
+
+def _first_conv(module):
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            return m
+    raise ValueError("module has no convolution to lower")
+
+
+# -------------------------------------------------------------------------------------------------------
+# autograd bridge: model(input) -> logits with loss.backward() filling param.grad (train.py:433-440)
+# -------------------------------------------------------------------------------------------------------
+class _ProgramFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, x, dropout_masks, *params):
+        plan = eng.forward(x, True, dropout_masks)
+        ctx.eng, ctx.plan, ctx.gen = eng, plan, plan.generation
+        ctx.x_needs_grad = x.requires_grad
+        if getattr(eng.module, "_mnb", None) == "net":
+            return plan.logits.clone()
+        return plan.out_nchw.clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng, plan = ctx.eng, ctx.plan
+        if plan.generation != ctx.gen:
+            raise RuntimeError("mnb200: the activations of this forward were overwritten by a later forward of "
+                               "the same shape; call backward before the next forward")
+        stream = torch.cuda.current_stream().cuda_stream
+        dout = dout.contiguous().float()
+        dx = None
+        if getattr(eng.module, "_mnb", None) == "net":
+            plan.dlogits.copy_(dout)
+        else:
+            o = plan.sub_out
+            check(lib.mnb_nchw_f32_to_nhwc(dout.data_ptr(), plan.sub_dout.data_ptr(), o.N, o.H, o.W, o.C, plan.code,
+                                           stream), "nchw_to_nhwc(grad)")
+        eng.backward(plan)
+        if getattr(eng.module, "_mnb", None) != "net" and ctx.x_needs_grad and plan.sub_din is not None:
+            dx = torch.empty_like(plan.cur_input)
+            N, C, H, W = dx.shape
+            check(lib.mnb_nhwc_to_nchw_f32(plan.sub_din.data_ptr(), dx.data_ptr(), N, H, W, C, plan.code, stream),
+                  "nhwc_to_nchw(grad)")
+        g = eng.store.grad.clone()                 # one copy; .grad tensors are views of it
+        views = eng.store.grad_views(g)
+        grads = tuple(views[id(p)] if p.requires_grad else None for p in eng.store.params)
+        return (None, dx, None) + grads
+
+
+_ENGINES = weakref.WeakKeyDictionary()
+_DEFAULTS = {"dtype": "bf16", "impl": "auto"}
+
+
+def configure(module: Optional[nn.Module] = None, dtype: Optional[str] = None, impl: Optional[str] = None):
+    """Select the activation dtype ("bf16" | "fp32") / GEMM implementation for a module (or the default for
+    modules lowered later).  Must be called before the first forward of that module."""
+    tgt = _DEFAULTS if module is None else module.__dict__.setdefault("_mnb_cfg", dict(_DEFAULTS))
+    if dtype is not None:
+        tgt["dtype"] = dtype
+    if impl is not None:
+        tgt["impl"] = impl
+    if module is not None and module in _ENGINES:
+        del _ENGINES[module]
+
+
+def engine_for(module: nn.Module) -> Engine:
+    eng = _ENGINES.get(module)
+    if eng is None:
+        cfg = module.__dict__.get("_mnb_cfg", _DEFAULTS)
+        p = next(module.parameters())
+        if not p.is_cuda:
+            raise RuntimeError("mnb200: move the model to a CUDA device first (model.to('cuda')); "
+                               "there is no CPU fallback")
+        eng = Engine(module, cfg["dtype"], cfg["impl"], device=p.device)
+        _ENGINES[module] = eng
+    return eng
+
+
+def run_module(module: nn.Module, x: torch.Tensor, dropout_masks=None) -> torch.Tensor:
+    """``module(x)`` for any lowered module (FineTuneModelPool, Mnasnet, MBConv, MBConv_block, SepConv,
+    ConvBlock): NCHW fp32 in, NCHW fp32 (or logits) out."""
+    _require_cuda()
+    eng = engine_for(module)
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in eng.store.params))
+    if module.training and needs_grad:
+        eng._check_store()
+        return _ProgramFn.apply(eng, x, dropout_masks, *eng.store.params)
+    if needs_grad and not module.training:
+        raise RuntimeError("mnb200: gradients through eval-mode (running-stat) BatchNorm are not lowered")
+    with torch.no_grad():
+        plan = eng.forward(x, module.training, dropout_masks)
+        if getattr(module, "_mnb", None) == "net":
+            return plan.logits.clone()
+        return plan.out_nchw.clone()
