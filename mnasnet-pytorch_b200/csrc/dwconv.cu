@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128) dw_fwd_k(const T* __restrict__ x, const f
     if (STATS) {
         __shared__ float red[4][32];
         const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-        if (tid < 128) (&red[0][0])[tid] = 0.f;
+        for (int i = tid; i < 4 * 32; i += blockDim.x * blockDim.y) (&red[0][0])[i] = 0.f;
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 4; ++q) atomicAdd(&red[q][threadIdx.x], st[q]);

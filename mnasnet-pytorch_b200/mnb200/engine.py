@@ -578,6 +578,7 @@ class Engine:
         self.dropout = "on"            # "on" | "off"
         self.grad_hook = None          # DDP: callable(engine, stage) invoked while backward is enqueued
         self.graphs = {}
+        self.world_size = 1
 
     def plan(self, N, H, W) -> Plan:
         key = (N, H, W)
@@ -643,9 +644,9 @@ class Engine:
             hook.run_backward(self, plan, stream)
 
     # ---- fused training step (train.py:433-440 entirely in libmnb200) -----------------------------
-    def train_step(self, x, target, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, allreduce=None, world_size=1):
-        """forward + CrossEntropyLoss(mean) + backward + Adam.  Returns the (device) loss tensor of shape [1].
-        `allreduce`: optional callable(engine) that averages self.store.grad across ranks (mnb200.ddp)."""
+    def train_step(self, x, target, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        """forward + CrossEntropyLoss(mean) + backward (+ bucketed all-reduce when a mnb200.ddp.GradSync is
+        attached) + Adam.  Returns the device loss tensor of shape [1] (this rank's mean loss)."""
         plan = self.forward(x, True)
         stream = torch.cuda.current_stream().cuda_stream
         plan.target.copy_(target, non_blocking=True)
@@ -654,21 +655,84 @@ class Engine:
                                    plan.dlogits.data_ptr(), plan.N, plan.num_out, 1.0, stream), "xent")
         self.backward(plan)
         gscale = 1.0
-        if allreduce is not None:
-            allreduce(self)
-            gscale = 1.0 / world_size
+        if self.grad_hook is not None:
+            self.grad_hook.wait()
+            gscale = 1.0 / self.grad_hook.world
         self.adam(lr, betas, eps, gscale)
         return plan.loss
 
-    def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, lr_on_device=False):
         stream = torch.cuda.current_stream().cuda_stream
         m, v = self.store.adam_state()
         self.host_step += 1
         check(lib.mnb_counter_inc(self.dev_step.data_ptr(), stream), "counter_inc")
         st = self.store
         check(lib.mnb_adam_step(st.flat.data_ptr(), st.grad.data_ptr(), m.data_ptr(), v.data_ptr(), st.total,
-                                float(lr), betas[0], betas[1], eps, self.host_step, grad_scale, None,
+                                float(lr), betas[0], betas[1], eps, self.host_step, grad_scale,
+                                self.dev_lr.data_ptr() if lr_on_device else None,
                                 self.dev_step.data_ptr(), stream), "adam")
+
+    # ---- CUDA-graph replay of the whole step (single GPU): ~450 launches -> one graph launch ---------
+    def train_step_graph(self, x, target, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        """Same as train_step, replayed from a CUDA graph captured per input shape.  x / target are copied
+        into static buffers; lr and the step counter are read from device scalars so the schedule can change
+        between replays (train.py:282-302,334)."""
+        if self.grad_hook is not None:
+            raise RuntimeError("graph replay is single-GPU; use train_step with GradSync for data parallel")
+        self._check_store()
+        N, C, H, W = x.shape
+        key = (N, H, W)
+        g = self.graphs.get(key)
+        if g is None:
+            plan = self.plan(N, H, W)
+            self.store.adam_state()
+            sx = torch.empty((N, C, H, W), device=self.device, dtype=torch.float32)
+            st = torch.zeros(N, device=self.device, dtype=torch.long)
+            sx.copy_(x)
+            st.copy_(target)
+            self.dev_lr.fill_(float(lr))
+            # one eager step on a side stream warms every kernel (and lazy module loading) before capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            saved = (self.store.flat.clone(), self.store.fbuf.clone(), self.store.ibuf.clone(),
+                     self.dev_step.clone(), self.host_step)
+            with torch.cuda.stream(s):
+                self._graph_body(sx, st, betas, eps)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.store.flat.copy_(saved[0]); self.store.fbuf.copy_(saved[1]); self.store.ibuf.copy_(saved[2])
+            self.dev_step.copy_(saved[3]); self.host_step = saved[4]
+            self.store.m.zero_(); self.store.v.zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._graph_body(sx, st, betas, eps)
+            # capture does not execute: state is untouched
+            g = (graph, sx, st, plan)
+            self.graphs[key] = g
+        graph, sx, st, plan = g
+        sx.copy_(x, non_blocking=True)
+        st.copy_(target, non_blocking=True)
+        self.dev_lr.fill_(float(lr))
+        graph.replay()
+        return plan.loss
+
+    def _graph_body(self, sx, st, betas, eps):
+        plan = self.forward(sx, True)
+        stream = torch.cuda.current_stream().cuda_stream
+        plan.target.copy_(st)
+        plan.loss.zero_()
+        check(lib.mnb_xent_fwd_bwd(plan.logits.data_ptr(), plan.target.data_ptr(), plan.loss.data_ptr(),
+                                   plan.dlogits.data_ptr(), plan.N, plan.num_out, 1.0, stream), "xent")
+        self.backward(plan)
+        self.adam(0.0, betas, eps, 1.0, lr_on_device=True)
+
+    def launches_per_step(self, N, H, W):
+        """Number of libmnb200 kernel launches in one fused training step of this shape."""
+        plan = self.plan(N, H, W)
+        n = 0
+        for op in plan.fwd + plan.bwd:
+            n += 2 if getattr(op, "name", "") == "mnb_fc_wgrad" else 1
+        return n + 3          # xent, counter_inc, adam
 
     def logits(self, plan):
         return plan.logits
