@@ -150,7 +150,7 @@ class ParamStore:
 class _ConvApp:
     """One application of a ConvBlock inside a plan."""
     __slots__ = ("cb", "inp", "z", "stats", "sums", "scale", "shift", "mean", "invstd", "coef", "kind",
-                 "Ho", "Wo", "Cout", "k", "stride", "pad", "need_dgrad", "m")
+                 "Ho", "Wo", "Cout", "k", "stride", "pad", "need_dgrad", "m", "in_bytes", "out_bytes", "label")
 
 
 class Plan:
@@ -160,6 +160,7 @@ class Plan:
         self.eng, self.N, self.H, self.W = eng, N, H, W
         self.dev = eng.device
         self.code, self.tdtype = DTYPES[eng.dtype]
+        self.esize = 4 if eng.dtype == "fp32" else 2
         self.keep = []              # tensors owned by the plan
         self.fwd, self.fwd_eval, self.bwd = [], [], []
         self.apps: List[_ConvApp] = []
@@ -232,7 +233,9 @@ class Plan:
                 r = self._emit(child, r)
             y = self._act(x.N, x.H, x.W, x.C)
             M = x.M
-            self._op(self.fwd, "mnb_bn_relu_apply", r.t, r.scale, r.shift, x.t, y, M, x.C, self.code)
+            nb = 3 * M * x.C * self.esize
+            self._op(self.fwd, "mnb_bn_relu_apply", r.t, r.scale, r.shift, x.t, y, M, x.C, self.code, nbytes=nb,
+                     label="bn_relu_apply+res")
             self._op(self.fwd_eval, "mnb_bn_relu_apply", r.t, r.scale, r.shift, x.t, y, M, x.C, self.code)
             self.tape.append(("res_end", x))
             return Ref(y, x.N, x.H, x.W, x.C)
@@ -249,7 +252,8 @@ class Plan:
             raise RuntimeError("NCHW input can only feed a dense ConvBlock")
         y = self._act(ref.N, ref.H, ref.W, ref.C)
         for ops in (self.fwd, self.fwd_eval):
-            self._op(ops, "mnb_bn_relu_apply", ref.t, ref.scale, ref.shift, None, y, ref.M, ref.C, self.code)
+            self._op(ops, "mnb_bn_relu_apply", ref.t, ref.scale, ref.shift, None, y, ref.M, ref.C, self.code,
+                     nbytes=2 * ref.M * ref.C * self.esize, label="bn_relu_apply")
         self.tape.append(("materialize", ref))
         return Ref(y, ref.N, ref.H, ref.W, ref.C)
 
@@ -277,14 +281,20 @@ class Plan:
         eng = self.eng
         x_t = ref.t if not ref.nchw else _InputPtr(self)
         layout = _lib.LAYOUT_NCHW_F32 if ref.nchw else _lib.LAYOUT_NHWC
+        es = self.esize
+        in_b = ref.M * cin * (4 if ref.nchw else es)
+        out_b = int(a.m) * cout * es
+        a.in_bytes, a.out_bytes = in_b, out_b
+        a.label = f"dw{k}x{k}" if a.kind == "dw" else (f"conv{k}x{k}" if k > 1 else "pw1x1")
         for ops, train in ((self.fwd, True), (self.fwd_eval, False)):
             st = a.stats if train else None
             if a.kind == "dense":
                 self._op(ops, "mnb_conv_fwd", x_t, ref.scale, ref.shift, conv.weight, conv.bias, a.z, st,
-                         ref.N, ref.H, ref.W, cin, cout, k, stride, pad, self.code, layout, eng.impl)
+                         ref.N, ref.H, ref.W, cin, cout, k, stride, pad, self.code, layout, eng.impl,
+                         nbytes=in_b + out_b, label=a.label + "_fwd")
             else:
                 self._op(ops, "mnb_dw_fwd", x_t, ref.scale, ref.shift, conv.weight, conv.bias, a.z, st,
-                         ref.N, ref.H, ref.W, cin, k, self.code)
+                         ref.N, ref.H, ref.W, cin, k, self.code, nbytes=in_b + out_b, label=a.label + "_fwd")
             if train:
                 self._op(ops, "mnb_bn_finalize", a.stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                          bn.num_batches_tracked, a.scale, a.shift, a.mean, a.invstd, cout, a.m,
@@ -391,10 +401,12 @@ class Plan:
                 conv, bn = a.cb.conv, a.cb.bn
                 M, C = int(a.m), a.Cout
                 dz = free.pop()
-                self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code)
+                self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
+                         nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
                 self._op(ops, "mnb_bn_bwd_finalize", a.sums, a.scale, a.mean, a.invstd, _G(bn.weight),
                          _G(bn.bias), _G(conv.bias), a.coef, C, a.m)
-                self._op(ops, "mnb_bn_bwd_apply", gbuf, a.z, a.scale, a.shift, a.coef, dz, M, C, self.code)
+                self._op(ops, "mnb_bn_bwd_apply", gbuf, a.z, a.scale, a.shift, a.coef, dz, M, C, self.code,
+                         nbytes=3 * a.out_bytes, label="bn_bwd_apply")
                 in_held = any(gbuf is h for h in held)
                 if not in_held:
                     free.append(gbuf)
@@ -403,10 +415,11 @@ class Plan:
                 layout = _lib.LAYOUT_NCHW_F32 if r.nchw else _lib.LAYOUT_NHWC
                 if a.kind == "dense":
                     self._op(ops, "mnb_conv_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W,
-                             r.C, C, a.k, a.stride, a.pad, self.code, layout, eng.impl)
+                             r.C, C, a.k, a.stride, a.pad, self.code, layout, eng.impl,
+                             nbytes=a.in_bytes + a.out_bytes, label=a.label + "_wgrad")
                 else:
                     self._op(ops, "mnb_dw_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W, r.C,
-                             a.k, self.code)
+                             a.k, self.code, nbytes=a.in_bytes + a.out_bytes, label=a.label + "_wgrad")
                 if a.need_dgrad:
                     dx = free.pop()
                     # the first conv of a residual block adds the skip gradient (dY) into its dgrad output
@@ -415,9 +428,12 @@ class Plan:
                         add = held[-1]
                     if a.kind == "dense":
                         self._op(ops, "mnb_conv_dgrad", dz, conv.weight, add, dx, r.N, r.H, r.W, r.C, C, a.k,
-                                 a.stride, a.pad, self.code, eng.impl)
+                                 a.stride, a.pad, self.code, eng.impl,
+                                 nbytes=a.in_bytes * (2 if add is not None else 1) + a.out_bytes,
+                                 label=a.label + "_dgrad")
                     else:
-                        self._op(ops, "mnb_dw_dgrad", dz, conv.weight, dx, r.N, r.H, r.W, r.C, a.k, self.code)
+                        self._op(ops, "mnb_dw_dgrad", dz, conv.weight, dx, r.N, r.H, r.W, r.C, a.k, self.code,
+                                 nbytes=a.in_bytes + a.out_bytes, label=a.label + "_dgrad")
                     free.append(dz)
                     gbuf = dx
                 else:
@@ -426,7 +442,7 @@ class Plan:
         self.sub_din = gbuf
 
     # ---- op plumbing -----------------------------------------------------------------------------------
-    def _op(self, ops, name, *args):
+    def _op(self, ops, name, *args, nbytes=0, label=None):
         fn = getattr(lib, name)
         conv = []
         if ops is self.bwd:
@@ -440,11 +456,23 @@ class Plan:
                 conv.append(_TensorPtr(a))
             else:
                 conv.append(a)
-        ops.append(_Op(name, fn, conv, self))
+        op = _Op(name, fn, conv, self)
+        op.nbytes, op.label = nbytes, label or name
+        ops.append(op)
 
     def run(self, ops, stream):
-        for op in ops:
+        prof = self.eng.profile
+        if prof is None:
+            for op in ops:
+                op(stream)
+            return
+        cur = torch.cuda.current_stream()
+        for op in ops:          # per-launch CUDA-event timing on the launching stream (bench.py roofline pass)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
             op(stream)
+            e1.record(cur)
+            prof.append((getattr(op, "label", op.name), getattr(op, "nbytes", 0), e0, e1))
 
 
 class _TensorPtr:
@@ -579,6 +607,7 @@ class Engine:
         self.grad_hook = None          # DDP: callable(engine, stage) invoked while backward is enqueued
         self.graphs = {}
         self.world_size = 1
+        self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
 
     def plan(self, N, H, W) -> Plan:
         key = (N, H, W)
@@ -779,7 +808,11 @@ class _ProgramFn(torch.autograd.Function):
             N, C, H, W = dx.shape
             check(lib.mnb_nhwc_to_nchw_f32(plan.sub_din.data_ptr(), dx.data_ptr(), N, H, W, C, plan.code, stream),
                   "nhwc_to_nchw(grad)")
-        g = eng.store.grad.clone()                 # one copy; .grad tensors are views of it
+        if eng.grad_hook is not None:              # data parallel: buckets were all-reduced during backward
+            eng.grad_hook.wait()
+            g = eng.store.grad / float(eng.grad_hook.world)
+        else:
+            g = eng.store.grad.clone()             # one copy; .grad tensors are views of it
         views = eng.store.grad_views(g)
         grads = tuple(views[id(p)] if p.requires_grad else None for p in eng.store.params)
         return (None, dx, None) + grads
