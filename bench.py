@@ -296,11 +296,15 @@ def main():
         torch.cuda.synchronize()
         rec, eng.profile, eng.grad_hook = eng.profile, None, hook
         agg = {}
-        for label, nbytes, a, b in rec:
+        per_op = {}
+        for label, nbytes, a, b, detail in rec:
             d = agg.setdefault(label, [0, 0.0, 0])
+            ms_ = a.elapsed_time(b)
             d[0] += 1
-            d[1] += a.elapsed_time(b)
+            d[1] += ms_
             d[2] += nbytes
+            q = per_op.setdefault((label, detail), [0, 0.0, 0])
+            q[0] += 1; q[1] += ms_; q[2] += nbytes
         tot = sum(v[1] for v in agg.values())
         table = sorted(({"kernel": k, "launches_per_step": v[0] // 3, "ms_per_step": v[1] / 3,
                          "share": v[1] / tot, "algorithmic_GB_per_step": v[2] / 3 / 1e9,
@@ -315,7 +319,11 @@ def main():
                 "step_frac_of_hbm_peak": (value / world) * 117.17e6 / 1e9 / hbm}
         if args.profile_out:
             with open(args.profile_out, "w") as f:
-                json.dump({"ms_per_step_sum": tot / 3, "kernels": table}, f, indent=1)
+                layers = sorted(({"kernel": k[0], "layer": k[1], "launches_per_step": v[0] // 3,
+                                  "ms_per_step": v[1] / 3, "algorithmic_GB_per_step": v[2] / 3 / 1e9,
+                                  "achieved_GBps": (v[2] / 1e9) / (v[1] / 1e3) if v[1] > 0 else 0.0}
+                                 for k, v in per_op.items()), key=lambda r: -r["ms_per_step"])
+                json.dump({"ms_per_step_sum": tot / 3, "kernels": table, "layers": layers[:80]}, f, indent=1)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

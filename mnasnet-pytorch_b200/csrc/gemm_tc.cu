@@ -11,8 +11,16 @@
 // with tcgen05.commit -> mbarrier.  The epilogue reads TMEM with tcgen05.ld (32x32b: thread == row), adds
 // bias / the residual gradient, rounds to bf16, stages the tile in shared memory, writes it out with
 // coalesced 16-byte stores and accumulates the BatchNorm sum / sum-of-squares of the stored values per column.
-// Several CTAs are resident per SM (<= 85 KB smem, <= 128 TMEM columns each) so one CTA's loads overlap
-// another's MMA / epilogue.  These GEMMs have K,N in 16..1152 and are HBM-bound.
+// The kernel is persistent (one 288-thread CTA per SM) and warp-specialised:
+//   warps 0-3  producers : thread == A row; cp.async (LDGSTS, zero-fill for padding) straight into the canonical
+//                          layout of a deep stage ring, D stages in flight per thread (memory-level parallelism),
+//                          then the BN-apply+ReLU prologue in place (ld.shared -> fp32 -> st.shared) and
+//                          fence.proxy.async + mbarrier arrive (full[s])
+//   warp  8    MMA issuer: waits full[s], issues tcgen05.mma, tcgen05.commit -> empty[s] / acc_full[a]
+//   warps 4-7  epilogue  : waits acc_full[a], drains one of the TWO TMEM accumulators, releases it (acc_empty[a])
+// so the loads of tile i+1 overlap the MMAs of tile i and the epilogue of tile i-1.  The weight operand stays
+// resident in shared memory across all M tiles of a CTA when it fits (N tile x K <= 48 K elements), otherwise it
+// is streamed with the A chunks.  These GEMMs have K,N in 16..1728 and are HBM-bound.
 //
 //   FWD    D[m=(n,ho,wo)][co]   = sum_kk a(m,kk) w(co,kk)      A,B K-major     kk = (kh,kw,ci)
 //   DGRAD  D[m=(n,h,w)][ci]     = sum_kk dz(m,kk) w(ci,kk)     A,B K-major     kk = (kh,kw,co)
@@ -26,6 +34,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 16-byte async copy global -> shared (LDGSTS); src_bytes == 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool pred) {
+    const uint32_t n = pred ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0, addr = smem_u32(bar);
@@ -84,338 +106,461 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-constexpr int KC = 64;            // K elements staged per chunk (4 MMAs of K=16)
-constexpr int TC_THREADS = 128;   // 4 warps: warp w reads TMEM lanes 32w..32w+31
+constexpr int KC = 64;             // max K elements staged per chunk (4 MMAs of K=16)
+constexpr int MAXSTAGE = 12;       // ring depth upper bound (barrier arrays)
+constexpr int TC_THREADS = 288;    // 4 producer warps + 4 epilogue warps + 1 MMA warp
+constexpr int B_RESIDENT_MAX = 40 * 1024;   // elements
 
 struct TcGeom {
-    int BN;          // N tile (multiple of 16, <= 128)
-    int n_tiles;     // tiles along N
-    int tmem_cols;   // power of two >= 32
+    int BN;            // N tile (multiple of 16, <= 128)
+    int n_tiles;       // tiles along N
+    int tmem_cols;     // power of two >= 32, holds 2 accumulators
     long long m_tiles;
-    int ksplit;      // wgrad: K splits
-    long long kchunks_per_split;
+    int ksplit;        // wgrad: K splits
+    long long cps;     // wgrad: chunks per split
+    int b_resident;    // fwd/dgrad: weight tile resident in smem
+    int kpad;          // K rounded up to 16 (resident B extent)
+    int kc;            // K elements per chunk (16..64; 64 for wgrad)
+    int nstage;        // ring depth = D + 2
+    int stage_bytes;
 };
 
-// ---- activation gather: 8 channels of a(n, ih, iw, ci..ci+7) -> packed bf16x8, transform optional --------
-__device__ __forceinline__ uint4 gather_act8(const ConvP& p, const float* s_scale, const float* s_shift, int n, int ih,
-                                             int iw, int ci) {
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) return u;      // zero padding applies to the ACTIVATION
-    u = *reinterpret_cast<const uint4*>((const bf16*)p.x + (((long long)n * p.H + ih) * p.W + iw) * p.Cin + ci);
-    if (s_scale) {
-        float v[8];
-        unpack_bf16x8(u, v);
-        float4 sa = *reinterpret_cast<const float4*>(s_scale + ci), sb = *reinterpret_cast<const float4*>(s_scale + ci + 4);
-        float4 ta = *reinterpret_cast<const float4*>(s_shift + ci), tb = *reinterpret_cast<const float4*>(s_shift + ci + 4);
-        v[0] = fmaxf(fmaf(sa.x, v[0], ta.x), 0.f); v[1] = fmaxf(fmaf(sa.y, v[1], ta.y), 0.f);
-        v[2] = fmaxf(fmaf(sa.z, v[2], ta.z), 0.f); v[3] = fmaxf(fmaf(sa.w, v[3], ta.w), 0.f);
-        v[4] = fmaxf(fmaf(sb.x, v[4], tb.x), 0.f); v[5] = fmaxf(fmaf(sb.y, v[5], tb.y), 0.f);
-        v[6] = fmaxf(fmaf(sb.z, v[6], tb.z), 0.f); v[7] = fmaxf(fmaf(sb.w, v[7], tb.w), 0.f);
-        u = pack_bf16x8(v);
-    }
-    return u;
+__device__ __forceinline__ uint4 xform8(uint4 u, const float* s_scale, const float* s_shift, int ci) {
+    float v[8];
+    unpack_bf16x8(u, v);
+    float4 sa = *reinterpret_cast<const float4*>(s_scale + ci), sb = *reinterpret_cast<const float4*>(s_scale + ci + 4);
+    float4 ta = *reinterpret_cast<const float4*>(s_shift + ci), tb = *reinterpret_cast<const float4*>(s_shift + ci + 4);
+    v[0] = fmaxf(fmaf(sa.x, v[0], ta.x), 0.f); v[1] = fmaxf(fmaf(sa.y, v[1], ta.y), 0.f);
+    v[2] = fmaxf(fmaf(sa.z, v[2], ta.z), 0.f); v[3] = fmaxf(fmaf(sa.w, v[3], ta.w), 0.f);
+    v[4] = fmaxf(fmaf(sb.x, v[4], tb.x), 0.f); v[5] = fmaxf(fmaf(sb.y, v[5], tb.y), 0.f);
+    v[6] = fmaxf(fmaf(sb.z, v[6], tb.z), 0.f); v[7] = fmaxf(fmaf(sb.w, v[7], tb.w), 0.f);
+    return pack_bf16x8(v);
 }
 
+// weight vector for the K-major B operand: 8 consecutive kk of column nn (fp32 torch layout -> bf16x8)
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_k(ConvP p, TcGeom g) {
+__device__ __forceinline__ uint4 load_w8(const ConvP& p, int kk2, int nn, int Ntot, long long kk, long long Ktot) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (nn < Ntot && kk < Ktot) {
+        if (MODE == MODE_FWD) {
+            const int tap = (int)(kk / p.Cin), ci = (int)(kk % p.Cin);
+            const float* wp = p.w + ((long long)nn * p.Cin + ci) * kk2 + tap;
+            if (kk2 == 1) load8(wp, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = wp[i * kk2];
+            }
+        } else {
+            const int tap = (int)(kk / p.Cout), co = (int)(kk % p.Cout);
+            const float* wp = p.w + ((long long)co * p.Cin + nn) * kk2 + tap;
+            const long long cs = (long long)p.Cin * kk2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = wp[i * cs];
+        }
+    }
+    return pack_bf16x8(v);
+}
+
+// Producer-side position in the (unit, chunk) sequence of this CTA.  Two of these walk the same sequence:
+// `issue` (cp.async) runs D chunks ahead of `finish` (in-place prologue + arrive).
+struct ChunkIt {
+    long long unit, c, cend, m0;
+    int n0, stage;
+    uint32_t ph;
+    int rn, rh, rw;      // decoded row (fwd/dgrad 3x3)
+    bool row_ok;
+};
+
+template <int MODE, int D>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int BN = g.BN;
     const int kk2 = p.k * p.k;
+    const int NST = g.nstage;
+    const int kc = g.kc;
     // ---- shared memory carve-up ----
-    unsigned char* sA = smem_raw;                               // 128 x KC bf16 = 16 KB
-    unsigned char* sB = sA + 128 * KC * 2;                      // BN x KC bf16
-    unsigned char* sC = sB + BN * KC * 2;                       // epilogue stage: 128 rows x (BN*2+16) B
+    unsigned char* sStage = smem_raw;                                         // NST x stage_bytes
+    unsigned char* sBres = sStage + NST * g.stage_bytes;                      // resident weights (fwd/dgrad)
+    const int bres_bytes = (MODE != MODE_WGRAD && g.b_resident) ? BN * g.kpad * 2 : 0;
+    unsigned char* sC = sBres + bres_bytes;                                   // epilogue stage
     const int c_pitch = BN * 2 + 16;
-    float* s_scale = reinterpret_cast<float*>(sC + 128 * c_pitch);
-    const int xch = (MODE == MODE_DGRAD) ? 0 : p.Cin;           // channels of the transformed operand
+    const int c_bytes = (MODE == MODE_WGRAD) ? 0 : 128 * c_pitch;
+    float* s_scale = reinterpret_cast<float*>(sC + c_bytes);
+    const int xch = (MODE == MODE_DGRAD) ? 0 : p.Cin;
     float* s_shift = s_scale + xch;
-    float* s_red = s_shift + xch;                               // [4][BN/2 * 2]... sized 2*BN floats
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(s_red + 2 * 256);
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(mbar + 1);
-
-    const bool xf = (MODE != MODE_DGRAD) && p.in_scale != nullptr;
-    if (xf)
-        for (int i = tid; i < p.Cin; i += TC_THREADS) { s_scale[i] = p.in_scale[i]; s_shift[i] = p.in_shift[i]; }
-    if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc(tmem_holder, (uint32_t)g.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const float* xs = xf ? s_scale : nullptr;
-    const float* xt = xf ? s_shift : nullptr;
+    float* s_bias = s_shift + xch;                                            // [128]
+    float* s_red = s_bias + 128;                                              // [2*128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 256);
+    uint64_t* full = bars;                     // [MAXSTAGE] producers -> MMA        (count 128)
+    uint64_t* empty = bars + MAXSTAGE;         // [MAXSTAGE] MMA commit -> producers (count 1)
+    uint64_t* acc_full = bars + 2 * MAXSTAGE;  // [2] MMA commit -> epilogue (count 1)
+    uint64_t* acc_empty = acc_full + 2;        // [2] epilogue -> MMA        (count 128)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    unsigned char* s_mask = reinterpret_cast<unsigned char*>(tmem_holder + 4);   // [MAXSTAGE][128]
 
     long long Mtot, Ktot;
     int Ntot;
     if (MODE == MODE_FWD) { Mtot = (long long)p.N * p.Ho * p.Wo; Ntot = p.Cout; Ktot = (long long)kk2 * p.Cin; }
     else if (MODE == MODE_DGRAD) { Mtot = (long long)p.N * p.H * p.W; Ntot = p.Cin; Ktot = (long long)kk2 * p.Cout; }
     else { Mtot = p.Cout; Ntot = kk2 * p.Cin; Ktot = (long long)p.N * p.Ho * p.Wo; }
+    const long long total_chunks = (Ktot + kc - 1) / kc;
+    const long long units = g.m_tiles * g.n_tiles * g.ksplit;
 
-    const uint32_t idesc = make_idesc(BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
-    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-    uint32_t phase = 0;
-    float st[4] = {0.f, 0.f, 0.f, 0.f};                         // FWD: per-thread column-pair statistics
-
-    const long long units = g.m_tiles * g.n_tiles * (MODE == MODE_WGRAD ? g.ksplit : 1);
-    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        long long u = unit;
-        int ks = 0;
-        if (MODE == MODE_WGRAD) { ks = (int)(u % g.ksplit); u /= g.ksplit; }
-        const int nt = (int)(u % g.n_tiles);
-        const long long mt = u / g.n_tiles;
-        const long long m0 = mt * 128;
-        const int n0 = nt * BN;
-        long long kbeg = 0, kend = Ktot;
-        if (MODE == MODE_WGRAD) {
-            kbeg = (long long)ks * g.kchunks_per_split * KC;
-            kend = kbeg + g.kchunks_per_split * KC;
-            if (kend > Ktot) kend = Ktot;
-            if (kbeg >= kend) continue;       // uniform across the CTA
+    // ---- one-time setup ----
+    const bool xf = (MODE != MODE_DGRAD) && p.in_scale != nullptr;
+    if (xf)
+        for (int i = tid; i < p.Cin; i += TC_THREADS) { s_scale[i] = p.in_scale[i]; s_shift[i] = p.in_shift[i]; }
+    const int nt_fixed = (int)((blockIdx.x / g.ksplit) % g.n_tiles);          // constant per CTA for fwd/dgrad
+    if (MODE == MODE_FWD)
+        for (int i = tid; i < 128; i += TC_THREADS)
+            s_bias[i] = (p.bias && nt_fixed * BN + i < Ntot && i < BN) ? p.bias[nt_fixed * BN + i] : 0.f;
+    if (MODE != MODE_WGRAD && g.b_resident) {
+        const int nk8 = g.kpad >> 3;
+        for (int vi = tid; vi < BN * nk8; vi += TC_THREADS) {
+            const int col = vi % BN, k8 = vi / BN;
+            *reinterpret_cast<uint4*>(sBres + ((k8 * BN) + col) * 16) =
+                load_w8<MODE>(p, kk2, nt_fixed * BN + col, Ntot, (long long)k8 * 8, Ktot);
         }
-        bool first = true;
-        for (long long k0 = kbeg; k0 < kend; k0 += KC) {
-            const int kvalid = (int)((kend - k0) < KC ? (kend - k0) : KC);
-            const int k16 = (kvalid + 15) / 16;                 // MMAs this chunk
+        fence_async_proxy();
+    }
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_holder, (uint32_t)g.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const bool is1x1 = (kk2 == 1 && p.stride == 1);
+
+    if (warp < 4) {
+        // =========================== PRODUCERS ===========================
+        auto setup_unit = [&](ChunkIt& it) {
+            if (it.unit >= units) return;
+            const int ks = (int)(it.unit % g.ksplit);
+            const int nt = (int)((it.unit / g.ksplit) % g.n_tiles);
+            const long long mt = it.unit / ((long long)g.ksplit * g.n_tiles);
+            it.m0 = mt * 128;
+            it.n0 = nt * BN;
+            long long cbeg = 0, cend = total_chunks;
+            if (MODE == MODE_WGRAD) { cbeg = ks * g.cps; cend = cbeg + g.cps < total_chunks ? cbeg + g.cps : total_chunks; }
+            it.c = cbeg;
+            it.cend = cend;
             if (MODE != MODE_WGRAD) {
-                // ---- K-major staging: vec(row, k8) -> ((k8*ROWS)+row)*16 ----
-                const int nk8 = k16 * 2;
-                // A: 16 row-blocks(8 rows) x 2 k8-blocks(4)
-                for (int idx = warp; idx < 32; idx += 4) {
-                    const int rb = idx >> 1, kb = idx & 1;
-                    const int row = rb * 8 + (lane & 7), k8 = kb * 4 + (lane >> 3);
-                    if (k8 >= nk8) continue;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    const long long m = m0 + row;
-                    const long long kk = k0 + k8 * 8;
-                    if (m < Mtot && kk < kend) {
-                        if (MODE == MODE_FWD) {
-                            const int wo = (int)(m % p.Wo), ho = (int)((m / p.Wo) % p.Ho);
-                            const int n = (int)(m / ((long long)p.Wo * p.Ho));
-                            const int tap = (int)(kk / p.Cin), ci = (int)(kk % p.Cin);
-                            const int kh = tap / p.k, kw = tap % p.k;
-                            v = gather_act8(p, xs, xt, n, ho * p.stride - p.pad + kh, wo * p.stride - p.pad + kw, ci);
-                        } else {
-                            const int w_ = (int)(m % p.W), h_ = (int)((m / p.W) % p.H);
-                            const int n = (int)(m / ((long long)p.W * p.H));
-                            const int tap = (int)(kk / p.Cout), co = (int)(kk % p.Cout);
-                            const int kh = tap / p.k, kw = tap % p.k;
-                            const int hn = h_ + p.pad - kh, wn = w_ + p.pad - kw;
-                            if (hn >= 0 && wn >= 0 && hn % p.stride == 0 && wn % p.stride == 0) {
-                                const int ho = hn / p.stride, wo = wn / p.stride;
-                                if (ho < p.Ho && wo < p.Wo)
-                                    v = *reinterpret_cast<const uint4*>(
-                                        (const bf16*)p.dz + (((long long)n * p.Ho + ho) * p.Wo + wo) * p.Cout + co);
-                            }
-                        }
-                    }
-                    *reinterpret_cast<uint4*>(sA + ((k8 * 128) + row) * 16) = v;
+                const long long m = it.m0 + tid;
+                it.row_ok = m < Mtot;
+                it.rn = it.rh = it.rw = 0;
+                if (it.row_ok && !is1x1) {
+                    const int Wd = MODE == MODE_FWD ? p.Wo : p.W, Hd = MODE == MODE_FWD ? p.Ho : p.H;
+                    it.rw = (int)(m % Wd); it.rh = (int)((m / Wd) % Hd); it.rn = (int)(m / ((long long)Wd * Hd));
                 }
-                // B: (BN/8) col-blocks x 2 k8-blocks
-                const int ncb = BN >> 3;
-                for (int idx = warp; idx < ncb * 2; idx += 4) {
-                    const int cb = idx >> 1, kb = idx & 1;
-                    const int col = cb * 8 + (lane & 7), k8 = kb * 4 + (lane >> 3);
-                    if (k8 >= nk8) continue;
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                    const int nn = n0 + col;
-                    const long long kk = k0 + k8 * 8;
-                    if (nn < Ntot && kk < kend) {
-                        if (MODE == MODE_FWD) {
-                            const int tap = (int)(kk / p.Cin), ci = (int)(kk % p.Cin);
-                            const float* wp = p.w + ((long long)nn * p.Cin + ci) * kk2 + tap;
-                            if (kk2 == 1) load8(wp, v);
-                            else {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = wp[i * kk2];
-                            }
+            }
+        };
+        auto advance = [&](ChunkIt& it) {
+            if (++it.stage == NST) { it.stage = 0; it.ph ^= 1; }
+            if (++it.c == it.cend) { it.unit += gridDim.x; setup_unit(it); }
+        };
+        // ---- issue: cp.async the raw vectors of one chunk into its stage (zero-fill where predicated off) ----
+        auto issue = [&](ChunkIt& it) {
+            mbar_wait(&empty[it.stage], it.ph ^ 1);
+            unsigned char* sA = sStage + it.stage * g.stage_bytes;
+            const long long k0 = it.c * kc;
+            const int kvalid = (int)((Ktot - k0) < kc ? (Ktot - k0) : kc);
+            unsigned mask = 0;
+            if (MODE != MODE_WGRAD) {
+                unsigned char* sB = sA + 128 * kc * 2;
+                const int nk8 = ((kvalid + 15) >> 4) << 1;
+                const int Cred = MODE == MODE_FWD ? p.Cin : p.Cout;           // channels per tap along K
+                const bf16* src0 = MODE == MODE_FWD ? (const bf16*)p.x : (const bf16*)p.dz;
+                const long long m = it.m0 + tid;
+                int tap = 0, cc = (int)k0;
+                if (!is1x1) { tap = (int)(k0 / Cred); cc = (int)(k0 % Cred); }
+                for (int k8 = 0; k8 < nk8; ++k8) {
+                    const bf16* src = src0;
+                    bool pred = it.row_ok && (k0 + k8 * 8 < Ktot);
+                    if (pred) {
+                        if (is1x1) {
+                            src = src0 + m * Cred + cc;
                         } else {
-                            const int tap = (int)(kk / p.Cout), co = (int)(kk % p.Cout);
-                            const float* wp = p.w + ((long long)co * p.Cin + nn) * kk2 + tap;
-                            const long long cs = (long long)p.Cin * kk2;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = wp[i * cs];
+                            const int kh = tap / p.k, kw = tap - kh * p.k;
+                            if (MODE == MODE_FWD) {
+                                const int ih = it.rh * p.stride - p.pad + kh, iw = it.rw * p.stride - p.pad + kw;
+                                pred = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+                                if (pred) src = src0 + (((long long)it.rn * p.H + ih) * p.W + iw) * p.Cin + cc;
+                            } else {
+                                const int hn = it.rh + p.pad - kh, wn = it.rw + p.pad - kw;
+                                pred = hn >= 0 && wn >= 0 && hn % p.stride == 0 && wn % p.stride == 0;
+                                if (pred) {
+                                    const int ho = hn / p.stride, wo = wn / p.stride;
+                                    pred = ho < p.Ho && wo < p.Wo;
+                                    if (pred) src = src0 + (((long long)it.rn * p.Ho + ho) * p.Wo + wo) * p.Cout + cc;
+                                }
+                            }
                         }
                     }
-                    *reinterpret_cast<uint4*>(sB + ((k8 * BN) + col) * 16) = pack_bf16x8(v);
+                    cp_async16(sA + ((k8 * 128) + tid) * 16, src, pred);
+                    mask |= (pred ? 1u : 0u) << k8;
+                    cc += 8;
+                    if (!is1x1 && cc >= Cred) { cc -= Cred; ++tap; }
+                }
+                if (!g.b_resident && tid < BN) {
+                    for (int k8 = 0; k8 < nk8; ++k8)
+                        *reinterpret_cast<uint4*>(sB + ((k8 * BN) + tid) * 16) =
+                            load_w8<MODE>(p, kk2, it.n0 + tid, Ntot, k0 + k8 * 8, Ktot);
                 }
             } else {
-                // ---- MN-major staging: vec(mn8, p) -> ((mn8*KC)+p)*16 ; K (=positions) zero-filled past kvalid ----
-                const int np8 = k16 * 2;                        // 8-position blocks that the MMAs will read
-                // A = dz^T : 16 mn8 (co/8) x KC positions ; combos: 8 p-blocks x 4 mn8-blocks
-                for (int idx = warp; idx < 32; idx += 4) {
-                    const int pb = idx & 7, mb = idx >> 3;
-                    if (pb >= np8) continue;
-                    const int pp = pb * 8 + (lane & 7), mn8 = mb * 4 + (lane >> 3);
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    const long long pos = k0 + pp;
-                    const long long co = m0 + mn8 * 8;
-                    if (pos < kend && co < Mtot)
-                        v = *reinterpret_cast<const uint4*>((const bf16*)p.dz + pos * p.Cout + co);
-                    *reinterpret_cast<uint4*>(sA + ((mn8 * KC) + pp) * 16) = v;
+                // MN-major: vec(mn8, pp) -> ((mn8*KC)+pp)*16 ; thread = (position pp, half)
+                unsigned char* sB = sA + 128 * KC * 2;
+                const int pp = tid & 63, half = tid >> 6;
+                const long long pos = k0 + pp;
+                const bool pos_ok = pos < Ktot;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {      // A = dz^T
+                    const int mn8 = half * 8 + j;
+                    const long long co = it.m0 + mn8 * 8;
+                    const bool pred = pos_ok && co < Mtot;
+                    cp_async16(sA + ((mn8 * KC) + pp) * 16, pred ? (const bf16*)p.dz + pos * p.Cout + co : (const bf16*)p.dz, pred);
                 }
-                // B = a^T : (BN/8) mn8 (kk/8) x KC positions
-                const int nmb = ((BN >> 3) + 3) >> 2;
-                for (int idx = warp; idx < 8 * nmb; idx += 4) {
-                    const int pb = idx & 7, mb = idx >> 3;
-                    if (pb >= np8) continue;
-                    const int pp = pb * 8 + (lane & 7), mn8 = mb * 4 + (lane >> 3);
-                    if (mn8 >= (BN >> 3)) continue;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    const long long pos = k0 + pp;
-                    const int kk = n0 + mn8 * 8;
-                    if (pos < kend && kk < Ntot) {
-                        const int wo = (int)(pos % p.Wo), ho = (int)((pos / p.Wo) % p.Ho);
-                        const int n = (int)(pos / ((long long)p.Wo * p.Ho));
-                        const int tap = kk / p.Cin, ci = kk % p.Cin;
-                        const int kh = tap / p.k, kw = tap % p.k;
-                        v = gather_act8(p, xs, xt, n, ho * p.stride - p.pad + kh, wo * p.stride - p.pad + kw, ci);
+                int wo = 0, ho = 0, n = 0;
+                if (pos_ok && !is1x1) {
+                    wo = (int)(pos % p.Wo); ho = (int)((pos / p.Wo) % p.Ho); n = (int)(pos / ((long long)p.Wo * p.Ho));
+                }
+                const int nmn = BN >> 3;
+                int b = 0;
+                for (int mn8 = half; mn8 < nmn; mn8 += 2, ++b) {   // B = a^T
+                    const int kk = it.n0 + mn8 * 8;
+                    const bf16* src = (const bf16*)p.x;
+                    bool pred = pos_ok && kk < Ntot;
+                    if (pred) {
+                        if (is1x1) src += pos * p.Cin + kk;
+                        else {
+                            const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
+                            const int kh = tap / p.k, kw = tap - kh * p.k;
+                            const int ih = ho * p.stride - p.pad + kh, iw = wo * p.stride - p.pad + kw;
+                            pred = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+                            if (pred) src += (((long long)n * p.H + ih) * p.W + iw) * p.Cin + ci;
+                        }
                     }
-                    *reinterpret_cast<uint4*>(sB + ((mn8 * KC) + pp) * 16) = v;
+                    cp_async16(sB + ((mn8 * KC) + pp) * 16, src, pred);
+                    mask |= (pred ? 1u : 0u) << b;
+                }
+            }
+            s_mask[it.stage * 128 + tid] = (unsigned char)mask;
+            cp_async_commit();
+        };
+        // ---- finish: BN-apply + ReLU in place on the vectors this thread copied, then publish the stage ----
+        auto finish = [&](ChunkIt& it) {
+            if (xf) {
+                unsigned char* sA = sStage + it.stage * g.stage_bytes;
+                unsigned mask = s_mask[it.stage * 128 + tid];
+                const long long k0 = it.c * kc;
+                if (MODE == MODE_FWD) {
+                    int cc = is1x1 ? (int)k0 : (int)(k0 % p.Cin);
+                    for (int k8 = 0; mask; ++k8, mask >>= 1) {
+                        if (mask & 1u) {
+                            uint4* q = reinterpret_cast<uint4*>(sA + ((k8 * 128) + tid) * 16);
+                            *q = xform8(*q, s_scale, s_shift, cc);
+                        }
+                        cc += 8;
+                        if (cc >= p.Cin) cc -= p.Cin;
+                    }
+                } else if (MODE == MODE_WGRAD) {
+                    unsigned char* sB = sA + 128 * KC * 2;
+                    const int pp = tid & 63, half = tid >> 6;
+                    for (int mn8 = half; mask; mn8 += 2, mask >>= 1) {
+                        if (mask & 1u) {
+                            const int kk = it.n0 + mn8 * 8;
+                            const int ci = is1x1 ? kk : kk % p.Cin;
+                            uint4* q = reinterpret_cast<uint4*>(sB + ((mn8 * KC) + pp) * 16);
+                            *q = xform8(*q, s_scale, s_shift, ci);
+                        }
+                    }
                 }
             }
             fence_async_proxy();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                for (int j = 0; j < k16; ++j) {
-                    uint64_t ad, bd;
-                    if (MODE != MODE_WGRAD) {
-                        ad = make_desc(sA_u + j * 2 * (128 * 16), 128 * 16, 128);
-                        bd = make_desc(sB_u + j * 2 * (BN * 16), BN * 16, 128);
-                    } else {
-                        ad = make_desc(sA_u + j * 256, 128, KC * 16);
-                        bd = make_desc(sB_u + j * 256, 128, KC * 16);
-                    }
-                    umma_bf16(tmem_base, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
-                }
-                umma_commit(mbar);
+            mbar_arrive(&full[it.stage]);
+        };
+        ChunkIt is, fs;
+        is.unit = fs.unit = blockIdx.x;
+        is.stage = fs.stage = 0;
+        is.ph = fs.ph = 0;
+        is.c = is.cend = fs.c = fs.cend = 0;
+        setup_unit(is);
+        setup_unit(fs);
+        int pending = 0;
+        while (is.unit < units) {
+            issue(is);
+            advance(is);
+            if (++pending > D) {
+                cp_async_wait<D>();
+                finish(fs);
+                advance(fs);
+                --pending;
             }
-            first = false;
-            mbar_wait(mbar, phase);           // MMAs done: smem reusable, accumulator up to date
-            phase ^= 1;
         }
-        tc_fence_after();
-        // ---- epilogue: thread == accumulator row ----
-        const long long row_g = m0 + tid;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        if (MODE == MODE_WGRAD) {
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(t_lane + c0, r);
-                if (row_g < Mtot) {
+        cp_async_wait<0>();
+        for (; pending > 0; --pending) { finish(fs); advance(fs); }
+    } else if (warp == 8) {
+        // =========================== MMA ISSUER ===========================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
+            int stage = 0, a = 0;
+            uint32_t ph = 0, aph = 0;
+            for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int ks = (int)(unit % g.ksplit);
+                long long cbeg = 0, cend = total_chunks;
+                if (MODE == MODE_WGRAD) { cbeg = ks * g.cps; cend = cbeg + g.cps < total_chunks ? cbeg + g.cps : total_chunks; }
+                mbar_wait(&acc_empty[a], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+                bool first = true;
+                for (long long c = cbeg; c < cend; ++c) {
+                    mbar_wait(&full[stage], ph);
+                    tc_fence_after();
+                    const uint32_t sA_u = smem_u32(sStage + stage * g.stage_bytes);
+                    const long long k0 = c * kc;
+                    const int kvalid = (int)((Ktot - k0) < kc ? (Ktot - k0) : kc);
+                    const int k16 = (kvalid + 15) >> 4;
+                    for (int j = 0; j < k16; ++j) {
+                        uint64_t ad, bd;
+                        if (MODE != MODE_WGRAD) {
+                            const uint32_t sB_u = sA_u + 128 * kc * 2;
+                            ad = make_desc(sA_u + j * 2 * (128 * 16), 128 * 16, 128);
+                            if (g.b_resident)
+                                bd = make_desc(smem_u32(sBres) + (uint32_t)((c * (kc >> 3) + j * 2) * BN * 16), BN * 16, 128);
+                            else
+                                bd = make_desc(sB_u + j * 2 * (BN * 16), BN * 16, 128);
+                        } else {
+                            const uint32_t sB_u = sA_u + 128 * KC * 2;
+                            ad = make_desc(sA_u + j * 256, 128, KC * 16);
+                            bd = make_desc(sB_u + j * 256, 128, KC * 16);
+                        }
+                        umma_bf16(d_tmem, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
+                    }
+                    first = false;
+                    umma_commit(&empty[stage]);
+                    if (++stage == NST) { stage = 0; ph ^= 1; }
+                }
+                umma_commit(&acc_full[a]);
+                if (++a == 2) { a = 0; aph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================== EPILOGUE ===========================
+        const int et = tid - 128;                      // accumulator row owned by this thread
+        const int ew = et >> 5;                        // == warp % 4 : TMEM lanes 32*ew .. 32*ew+31
+        int a = 0;
+        uint32_t aph = 0;
+        float st[4] = {0.f, 0.f, 0.f, 0.f};
+        const int ncp = BN >> 1;
+        const int groups = 128 / ncp;
+        const int cpi = et % ncp, rg = et / ncp;
+        for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            const int nt = (int)((unit / g.ksplit) % g.n_tiles);
+            const long long mt = unit / ((long long)g.ksplit * g.n_tiles);
+            const long long m0 = mt * 128;
+            const int n0 = nt * BN;
+            mbar_wait(&acc_full[a], aph);
+            tc_fence_after();
+            const long long row_g = m0 + et;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN);
+            if (MODE == MODE_WGRAD) {
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(t_lane + c0, r);
+                    if (row_g < Mtot) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int kk = n0 + c0 + j;
-                        if (kk < Ntot) {
-                            const int tap = kk / p.Cin, ci = kk % p.Cin;
-                            atomicAdd(&p.dw[((long long)row_g * p.Cin + ci) * kk2 + tap], __uint_as_float(r[j]));
+                        for (int j = 0; j < 16; ++j) {
+                            const int kk = n0 + c0 + j;
+                            if (kk < Ntot) {
+                                const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
+                                atomicAdd(&p.dw[((long long)row_g * p.Cin + ci) * kk2 + tap], __uint_as_float(r[j]));
+                            }
                         }
                     }
                 }
-            }
-        } else {
-            const int ldo = (MODE == MODE_FWD) ? p.Cout : p.Cin;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(t_lane + c0, r);
-                float v[16];
+                tc_fence_before();
+                mbar_arrive(&acc_empty[a]);
+            } else {
+                const int ldo = (MODE == MODE_FWD) ? p.Cout : p.Cin;
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(t_lane + c0, r);
+                    float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                if (MODE == MODE_FWD) {
-                    if (p.bias) {
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    if (MODE == MODE_FWD) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += (n0 + c0 + j < Ntot) ? p.bias[n0 + c0 + j] : 0.f;
+                        for (int j = 0; j < 16; ++j) v[j] += s_bias[c0 + j];
+                    } else if (p.add && row_g < Mtot) {
+                        const bf16* ap = (const bf16*)p.add + row_g * ldo + n0 + c0;
+                        if (n0 + c0 + 16 <= Ntot) {
+                            float a0[8], a1[8];
+                            load8(ap, a0);
+                            load8(ap + 8, a1);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
+                        } else {
+                            for (int j = 0; j < 16; ++j)
+                                if (n0 + c0 + j < Ntot) v[j] += to_f(ap[j]);
+                        }
                     }
-                } else if (p.add && row_g < Mtot) {
-                    const bf16* ap = (const bf16*)p.add + row_g * ldo + n0 + c0;
-                    if (n0 + c0 + 16 <= Ntot) {
-                        float a0[8], a1[8];
-                        load8(ap, a0);
-                        load8(ap + 8, a1);
+                    float lo[8], hi[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
-                    } else {
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + c0 + j < Ntot) v[j] += to_f(ap[j]);
-                    }
+                    for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+                    unsigned char* dst = sC + et * c_pitch + c0 * 2;
+                    *reinterpret_cast<uint4*>(dst) = pack_bf16x8(lo);
+                    *reinterpret_cast<uint4*>(dst + 16) = pack_bf16x8(hi);
                 }
-                float lo[8], hi[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-                unsigned char* dst = sC + tid * c_pitch + c0 * 2;
-                *reinterpret_cast<uint4*>(dst) = pack_bf16x8(lo);
-                *reinterpret_cast<uint4*>(dst + 16) = pack_bf16x8(hi);
-            }
-            tc_fence_before();
-            __syncthreads();
-            // coalesced write-out of the staged tile
-            const int vpr = BN >> 3;                            // 16-B vectors per row
-            for (int vi = tid; vi < 128 * vpr; vi += TC_THREADS) {
-                const int row = vi / vpr, c8 = vi % vpr;
-                const long long m = m0 + row;
-                const int col = n0 + c8 * 8;
-                if (m < Mtot && col < Ntot) {                   // Ntot % 8 == 0
-                    uint4 q = *reinterpret_cast<const uint4*>(sC + row * c_pitch + c8 * 16);
-                    *reinterpret_cast<uint4*>((bf16*)p.out + m * ldo + col) = q;
+                tc_fence_before();
+                mbar_arrive(&acc_empty[a]);            // accumulator drained: the MMA warp may reuse it
+                named_bar_sync(1, 128);
+                // coalesced write-out of the staged tile
+                const int vpr = BN >> 3;
+                for (int vi = et; vi < 128 * vpr; vi += 128) {
+                    const int row = vi / vpr, c8 = vi - row * vpr;
+                    const long long mm = m0 + row;
+                    const int col = n0 + c8 * 8;
+                    if (mm < Mtot && col < Ntot)
+                        *reinterpret_cast<uint4*>((bf16*)p.out + mm * ldo + col) =
+                            *reinterpret_cast<const uint4*>(sC + row * c_pitch + c8 * 16);
                 }
-            }
-            if (MODE == MODE_FWD && p.stats) {
-                // column-pair owner threads: sum / sum of squares of the STORED (bf16-rounded) values
-                const int ncp = BN >> 1;                        // <= 128 column pairs
-                const int groups = TC_THREADS / ncp;            // row groups sharing a column pair
-                const int cpi = tid % ncp, rg = tid / ncp;
-                if (rg < groups) {
+                if (MODE == MODE_FWD && p.stats && rg < groups) {
+                    // column-pair owner threads: sum / sum of squares of the STORED (bf16-rounded) values
                     const int rows_here = (int)(Mtot - m0 < 128 ? Mtot - m0 : 128);
                     for (int row = rg; row < rows_here; row += groups) {
-                        uint32_t w2 = *reinterpret_cast<const uint32_t*>(sC + row * c_pitch + cpi * 4);
-                        float a = __uint_as_float(w2 << 16), b = __uint_as_float(w2 & 0xffff0000u);
-                        st[0] += a; st[1] += b;
-                        st[2] = fmaf(a, a, st[2]); st[3] = fmaf(b, b, st[3]);
+                        const uint32_t w2 = *reinterpret_cast<const uint32_t*>(sC + row * c_pitch + cpi * 4);
+                        const float x0 = __uint_as_float(w2 << 16), x1 = __uint_as_float(w2 & 0xffff0000u);
+                        st[0] += x0; st[1] += x1;
+                        st[2] = fmaf(x0, x0, st[2]); st[3] = fmaf(x1, x1, st[3]);
                     }
                 }
+                named_bar_sync(1, 128);                // stage buffer free for the next tile
             }
+            if (++a == 2) { a = 0; aph ^= 1; }
         }
-        tc_fence_before();
-        __syncthreads();      // TMEM + stage buffer free for the next unit
-        tc_fence_after();
-        if (MODE == MODE_FWD && p.stats && g.n_tiles > 1) {
-            // the column assignment changes with the N tile: flush per unit
-            const int ncp = BN >> 1;
-            for (int i = tid; i < 2 * BN; i += TC_THREADS) s_red[i] = 0.f;
-            __syncthreads();
-            if (tid / ncp < TC_THREADS / ncp) {
-                const int cpi = tid % ncp;
+        if (MODE == MODE_FWD && p.stats) {
+            // the N tile is fixed per CTA: one flush at the end
+            for (int i = et; i < 2 * BN; i += 128) s_red[i] = 0.f;
+            named_bar_sync(1, 128);
+            if (rg < groups) {
                 atomicAdd(&s_red[cpi * 2], st[0]); atomicAdd(&s_red[cpi * 2 + 1], st[1]);
                 atomicAdd(&s_red[BN + cpi * 2], st[2]); atomicAdd(&s_red[BN + cpi * 2 + 1], st[3]);
             }
-            st[0] = st[1] = st[2] = st[3] = 0.f;
-            __syncthreads();
-            for (int i = tid; i < BN; i += TC_THREADS)
+            named_bar_sync(1, 128);
+            const int n0 = nt_fixed * BN;
+            for (int i = et; i < BN; i += 128)
                 if (n0 + i < Ntot) {
                     atomicAdd(&p.stats[n0 + i], (double)s_red[i]);
                     atomicAdd(&p.stats[p.Cout + n0 + i], (double)s_red[BN + i]);
                 }
-            __syncthreads();
         }
-    }
-    if (MODE == MODE_FWD && p.stats && g.n_tiles == 1) {
-        const int ncp = BN >> 1;
-        for (int i = tid; i < 2 * BN; i += TC_THREADS) s_red[i] = 0.f;
-        __syncthreads();
-        if (tid / ncp < TC_THREADS / ncp) {
-            const int cpi = tid % ncp;
-            atomicAdd(&s_red[cpi * 2], st[0]); atomicAdd(&s_red[cpi * 2 + 1], st[1]);
-            atomicAdd(&s_red[BN + cpi * 2], st[2]); atomicAdd(&s_red[BN + cpi * 2 + 1], st[3]);
-        }
-        __syncthreads();
-        for (int i = tid; i < BN; i += TC_THREADS)
-            if (i < Ntot) {
-                atomicAdd(&p.stats[i], (double)s_red[i]);
-                atomicAdd(&p.stats[p.Cout + i], (double)s_red[BN + i]);
-            }
     }
     tc_fence_before();
     __syncthreads();
@@ -428,26 +573,66 @@ static int pow2_cols(int n) {
     return c;
 }
 
-static bool tc_geom(int mode, const ConvP& p, TcGeom& g, size_t& smem) {
+static bool tc_geom(int mode, const ConvP& p, TcGeom& g, size_t& smem, int& depth) {
     const int kk2 = p.k * p.k;
-    long long M;
+    long long M, K;
     int Nn;
-    if (mode == MODE_FWD) { M = (long long)p.N * p.Ho * p.Wo; Nn = p.Cout; }
-    else if (mode == MODE_DGRAD) { M = (long long)p.N * p.H * p.W; Nn = p.Cin; }
-    else { M = p.Cout; Nn = kk2 * p.Cin; }
+    if (mode == MODE_FWD) { M = (long long)p.N * p.Ho * p.Wo; Nn = p.Cout; K = (long long)kk2 * p.Cin; }
+    else if (mode == MODE_DGRAD) { M = (long long)p.N * p.H * p.W; Nn = p.Cin; K = (long long)kk2 * p.Cout; }
+    else { M = p.Cout; Nn = kk2 * p.Cin; K = (long long)p.N * p.Ho * p.Wo; }
     if (p.nchw_in || p.Cin % 8 != 0 || p.Cout % 8 != 0) return false;
-    int nt = (Nn + 127) / 128;
-    int BN = ((Nn + nt - 1) / nt + 15) / 16 * 16;
+    const int nt = (Nn + 127) / 128;
+    const int BN = ((Nn + nt - 1) / nt + 15) / 16 * 16;
     g.BN = BN;
     g.n_tiles = (Nn + BN - 1) / BN;
-    g.tmem_cols = pow2_cols(BN);
+    g.tmem_cols = pow2_cols(2 * BN);
     g.m_tiles = (M + 127) / 128;
     g.ksplit = 1;
-    g.kchunks_per_split = 0;
+    g.cps = 0;
+    g.kpad = (int)((K + 15) / 16 * 16);
+    g.b_resident = (mode != MODE_WGRAD) && ((long long)BN * g.kpad <= B_RESIDENT_MAX);
+    g.kc = (mode == MODE_WGRAD) ? KC : (g.kpad < KC ? g.kpad : KC);
+    g.stage_bytes = 128 * g.kc * 2 + ((mode == MODE_WGRAD || !g.b_resident) ? BN * g.kc * 2 : 0);
     const int xch = mode == MODE_DGRAD ? 0 : p.Cin;
-    smem = (size_t)128 * KC * 2 + (size_t)BN * KC * 2 + (size_t)128 * (BN * 2 + 16) + (size_t)2 * xch * 4 +
-           2 * 256 * 4 + 64;
-    return true;
+    const size_t fixed = (g.b_resident ? (size_t)BN * g.kpad * 2 : 0) +
+                         (mode == MODE_WGRAD ? 0 : (size_t)128 * (BN * 2 + 16)) + (size_t)2 * xch * 4 + (128 + 256) * 4 +
+                         (2 * MAXSTAGE + 4) * 8 + 16 + MAXSTAGE * 128 + 128;
+    // deep ring of small stages when the chunk is small (memory-level parallelism), else 5 x up to 32 KB
+    depth = ((size_t)10 * g.stage_bytes + fixed <= 220 * 1024) ? 8 : 3;
+    g.nstage = depth + 2;
+    smem = (size_t)g.nstage * g.stage_bytes + fixed;
+    return smem <= 227 * 1024;
+}
+
+template <int MODE, int D>
+static int launch_tc_d(const ConvP& p, TcGeom& g, size_t smem, cudaStream_t st, const char* name) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_k<MODE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
+        attr_done = true;
+    }
+    const long long slots = num_sms();
+    long long tiles = g.m_tiles * g.n_tiles;
+    long long grid;
+    if (MODE == MODE_WGRAD) {
+        const long long K = (long long)p.N * p.Ho * p.Wo;
+        const long long chunks = (K + KC - 1) / KC;
+        long long want = slots / tiles;
+        if (want < 1) want = 1;
+        if (want > chunks) want = chunks;
+        g.cps = (chunks + want - 1) / want;
+        g.ksplit = (int)((chunks + g.cps - 1) / g.cps);
+        tiles *= g.ksplit;
+        grid = tiles < slots ? tiles : slots;
+    } else {
+        // grid must be a multiple of n_tiles so that a CTA keeps one N tile (resident weights, fixed stats columns)
+        grid = tiles < slots ? tiles : slots / g.n_tiles * g.n_tiles;
+        if (grid < g.n_tiles) grid = g.n_tiles;
+    }
+    conv_tc_k<MODE, D><<<(unsigned)grid, TC_THREADS, smem, st>>>(p, g);
+    MNB_LAUNCH_CHECK(name);
+    return 0;
 }
 
 template <int MODE>
@@ -455,34 +640,10 @@ static int launch_tc(const ConvP& p, cudaStream_t st, const char* name) {
     if (!mnb_device_is_sm100()) { set_error("%s: device is not sm_100", name); return MNB_ERR_UNSUPPORTED; }
     TcGeom g;
     size_t smem;
-    if (!tc_geom(MODE, p, g, smem)) { set_error("%s: shape not covered", name); return MNB_ERR_UNSUPPORTED; }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
-        attr_done = true;
-    }
-    const int sms = num_sms();
-    int ctas_per_sm = (int)(200 * 1024 / (smem + 1024));
-    if (ctas_per_sm > 512 / g.tmem_cols) ctas_per_sm = 512 / g.tmem_cols;
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    long long slots = (long long)sms * ctas_per_sm;
-    long long tiles = g.m_tiles * g.n_tiles;
-    if (MODE == MODE_WGRAD) {
-        long long K = (long long)p.N * p.Ho * p.Wo;
-        long long chunks = (K + KC - 1) / KC;
-        long long want = slots / tiles;
-        if (want < 1) want = 1;
-        if (want > chunks) want = chunks;
-        g.kchunks_per_split = (chunks + want - 1) / want;
-        g.ksplit = (int)((chunks + g.kchunks_per_split - 1) / g.kchunks_per_split);
-        tiles *= g.ksplit;
-    }
-    long long grid = tiles < slots ? tiles : slots;
-    conv_tc_k<MODE><<<(unsigned)grid, TC_THREADS, smem, st>>>(p, g);
-    MNB_LAUNCH_CHECK(name);
-    return 0;
+    int depth;
+    if (!tc_geom(MODE, p, g, smem, depth)) { set_error("%s: shape not covered", name); return MNB_ERR_UNSUPPORTED; }
+    if (depth == 8) return launch_tc_d<MODE, 8>(p, g, smem, st, name);
+    return launch_tc_d<MODE, 3>(p, g, smem, st, name);
 }
 
 int conv_fwd_tc(const ConvP& p, cudaStream_t st) { return launch_tc<MODE_FWD>(p, st, "conv_fwd(tcgen05)"); }

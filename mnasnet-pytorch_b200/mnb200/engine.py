@@ -286,6 +286,7 @@ class Plan:
         out_b = int(a.m) * cout * es
         a.in_bytes, a.out_bytes = in_b, out_b
         a.label = f"dw{k}x{k}" if a.kind == "dw" else (f"conv{k}x{k}" if k > 1 else "pw1x1")
+        self._cur_detail = f"{ref.H}x{ref.W} {cin}->{cout} k{k}s{stride}"
         for ops, train in ((self.fwd, True), (self.fwd_eval, False)):
             st = a.stats if train else None
             if a.kind == "dense":
@@ -400,6 +401,7 @@ class Plan:
                 a = entry[1]
                 conv, bn = a.cb.conv, a.cb.bn
                 M, C = int(a.m), a.Cout
+                self._cur_detail = f"{a.inp.H}x{a.inp.W} {a.inp.C}->{a.Cout} k{a.k}s{a.stride}"
                 dz = free.pop()
                 self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
                          nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
@@ -458,6 +460,7 @@ class Plan:
                 conv.append(a)
         op = _Op(name, fn, conv, self)
         op.nbytes, op.label = nbytes, label or name
+        op.detail = getattr(self, "_cur_detail", "")
         ops.append(op)
 
     def run(self, ops, stream):
@@ -472,7 +475,8 @@ class Plan:
             e0.record(cur)
             op(stream)
             e1.record(cur)
-            prof.append((getattr(op, "label", op.name), getattr(op, "nbytes", 0), e0, e1))
+            prof.append((getattr(op, "label", op.name), getattr(op, "nbytes", 0), e0, e1,
+                         getattr(op, "detail", "")))
 
 
 class _TensorPtr:
