@@ -12,12 +12,13 @@
 // bias / the residual gradient, rounds to bf16, stages the tile in shared memory, writes it out with
 // coalesced 16-byte stores and accumulates the BatchNorm sum / sum-of-squares of the stored values per column.
 // The kernel is persistent (one 288-thread CTA per SM) and warp-specialised:
-//   warps 0-3  producers : thread == A row; cp.async (LDGSTS, zero-fill for padding) straight into the canonical
+//   warps 0-7  producers : thread == half an A row; cp.async (LDGSTS, zero-fill for padding) straight into the canonical
 //                          layout of a deep stage ring, D stages in flight per thread (memory-level parallelism),
 //                          then the BN-apply+ReLU prologue in place (ld.shared -> fp32 -> st.shared) and
 //                          fence.proxy.async + mbarrier arrive (full[s])
-//   warp  8    MMA issuer: waits full[s], issues tcgen05.mma, tcgen05.commit -> empty[s] / acc_full[a]
-//   warps 4-7  epilogue  : waits acc_full[a], drains one of the TWO TMEM accumulators, releases it (acc_empty[a])
+//   warp  16   MMA issuer: waits full[s], issues tcgen05.mma, tcgen05.commit -> empty[s] / acc_full[a]
+//   warps 8-15 epilogue  : two groups of 4 warps alternate tiles; group g waits acc_full[g], drains TMEM
+//                          accumulator g (tcgen05.ld), releases it (acc_empty[g]), stages, writes out + BN statistics
 // so the loads of tile i+1 overlap the MMAs of tile i and the epilogue of tile i-1.  The weight operand stays
 // resident in shared memory across all M tiles of a CTA when it fits (N tile x K <= 48 K elements), otherwise it
 // is streamed with the A chunks.  These GEMMs have K,N in 16..1728 and are HBM-bound.
@@ -92,8 +93,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 64-bit shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -108,8 +109,8 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
 
 constexpr int KC = 64;             // max K elements staged per chunk (4 MMAs of K=16)
 constexpr int MAXSTAGE = 12;       // ring depth upper bound (barrier arrays)
-constexpr int TC_THREADS = 288;    // 4 producer warps + 4 epilogue warps + 1 MMA warp
-constexpr int B_RESIDENT_MAX = 40 * 1024;   // elements
+constexpr int TC_THREADS = 544;    // 8 producer warps + 2 x 4 epilogue warps + 1 MMA warp
+constexpr int B_RESIDENT_MAX = 32 * 1024;   // elements
 
 struct TcGeom {
     int BN;            // N tile (multiple of 16, <= 128)
@@ -188,18 +189,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     unsigned char* sC = sBres + bres_bytes;                                   // epilogue stage
     const int c_pitch = BN * 2 + 16;
     const int c_bytes = (MODE == MODE_WGRAD) ? 0 : 128 * c_pitch;
-    float* s_scale = reinterpret_cast<float*>(sC + c_bytes);
+    float* s_scale = reinterpret_cast<float*>(sC + 2 * c_bytes);
     const int xch = (MODE == MODE_DGRAD) ? 0 : p.Cin;
     float* s_shift = s_scale + xch;
     float* s_bias = s_shift + xch;                                            // [128]
-    float* s_red = s_bias + 128;                                              // [2*128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 256);
-    uint64_t* full = bars;                     // [MAXSTAGE] producers -> MMA        (count 128)
+    float* s_red = s_bias + 128;                                              // [2 groups][2*128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 512);
+    uint64_t* full = bars;                     // [MAXSTAGE] producers -> MMA        (count 256)
     uint64_t* empty = bars + MAXSTAGE;         // [MAXSTAGE] MMA commit -> producers (count 1)
     uint64_t* acc_full = bars + 2 * MAXSTAGE;  // [2] MMA commit -> epilogue (count 1)
     uint64_t* acc_empty = acc_full + 2;        // [2] epilogue -> MMA        (count 128)
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    unsigned char* s_mask = reinterpret_cast<unsigned char*>(tmem_holder + 4);   // [MAXSTAGE][128]
+    unsigned char* s_mask = reinterpret_cast<unsigned char*>(tmem_holder + 4);   // [MAXSTAGE][256]
 
     long long Mtot, Ktot;
     int Ntot;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
         fence_async_proxy();
     }
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 256); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_mbar_init();
     }
@@ -238,8 +239,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     const uint32_t tmem_base = *tmem_holder;
     const bool is1x1 = (kk2 == 1 && p.stride == 1);
 
-    if (warp < 4) {
-        // =========================== PRODUCERS ===========================
+    if (warp < 8) {
+        // =========================== PRODUCERS (8 warps) ===========================
+        // fwd/dgrad: thread = (A row tid&127, k-parity tid>>7) and owns vectors k8 = 2i + parity, i < 4
+        // wgrad    : thread = (position tid&63, quarter tid>>6) and owns 4 A vectors + up to 4 B vectors
+        const int prow = tid & 127, ppar = tid >> 7;
+        const int wpp = tid & 63, wq = tid >> 6;
         auto setup_unit = [&](ChunkIt& it) {
             if (it.unit >= units) return;
             const int ks = (int)(it.unit % g.ksplit);
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
             it.c = cbeg;
             it.cend = cend;
             if (MODE != MODE_WGRAD) {
-                const long long m = it.m0 + tid;
+                const long long m = it.m0 + prow;
                 it.row_ok = m < Mtot;
                 it.rn = it.rh = it.rw = 0;
                 if (it.row_ok && !is1x1) {
@@ -277,17 +282,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                 const int nk8 = ((kvalid + 15) >> 4) << 1;
                 const int Cred = MODE == MODE_FWD ? p.Cin : p.Cout;           // channels per tap along K
                 const bf16* src0 = MODE == MODE_FWD ? (const bf16*)p.x : (const bf16*)p.dz;
-                const long long m = it.m0 + tid;
-                int tap = 0, cc = (int)k0;
-                if (!is1x1) { tap = (int)(k0 / Cred); cc = (int)(k0 % Cred); }
-                for (int k8 = 0; k8 < nk8; ++k8) {
+                const long long m = it.m0 + prow;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k8 = 2 * i + ppar;
+                    if (k8 >= nk8) continue;
+                    const long long kk = k0 + k8 * 8;
                     const bf16* src = src0;
-                    bool pred = it.row_ok && (k0 + k8 * 8 < Ktot);
+                    bool pred = it.row_ok && kk < Ktot;
                     if (pred) {
                         if (is1x1) {
-                            src = src0 + m * Cred + cc;
+                            src = src0 + m * Cred + kk;
                         } else {
-                            const int kh = tap / p.k, kw = tap - kh * p.k;
+                            const int tap = (int)(kk / Cred), cc = (int)(kk - (long long)tap * Cred);
+                            const int kh = tap / 3, kw = tap - kh * 3;                 // k == 3 whenever !is1x1
                             if (MODE == MODE_FWD) {
                                 const int ih = it.rh * p.stride - p.pad + kh, iw = it.rw * p.stride - p.pad + kw;
                                 pred = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
@@ -303,36 +311,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                             }
                         }
                     }
-                    cp_async16(sA + ((k8 * 128) + tid) * 16, src, pred);
-                    mask |= (pred ? 1u : 0u) << k8;
-                    cc += 8;
-                    if (!is1x1 && cc >= Cred) { cc -= Cred; ++tap; }
+                    cp_async16(sA + ((k8 * 128) + prow) * 16, src, pred);
+                    mask |= (pred ? 1u : 0u) << i;
                 }
-                if (!g.b_resident && tid < BN) {
-                    for (int k8 = 0; k8 < nk8; ++k8)
-                        *reinterpret_cast<uint4*>(sB + ((k8 * BN) + tid) * 16) =
-                            load_w8<MODE>(p, kk2, it.n0 + tid, Ntot, k0 + k8 * 8, Ktot);
+                if (!g.b_resident && prow < BN) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k8 = 2 * i + ppar;
+                        if (k8 < nk8)
+                            *reinterpret_cast<uint4*>(sB + ((k8 * BN) + prow) * 16) =
+                                load_w8<MODE>(p, kk2, it.n0 + prow, Ntot, k0 + k8 * 8, Ktot);
+                    }
                 }
             } else {
-                // MN-major: vec(mn8, pp) -> ((mn8*KC)+pp)*16 ; thread = (position pp, half)
+                // MN-major: vec(mn8, pp) -> ((mn8*KC)+pp)*16
                 unsigned char* sB = sA + 128 * KC * 2;
-                const int pp = tid & 63, half = tid >> 6;
-                const long long pos = k0 + pp;
+                const long long pos = k0 + wpp;
                 const bool pos_ok = pos < Ktot;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {      // A = dz^T
-                    const int mn8 = half * 8 + j;
+                for (int j = 0; j < 4; ++j) {      // A = dz^T
+                    const int mn8 = wq * 4 + j;
                     const long long co = it.m0 + mn8 * 8;
                     const bool pred = pos_ok && co < Mtot;
-                    cp_async16(sA + ((mn8 * KC) + pp) * 16, pred ? (const bf16*)p.dz + pos * p.Cout + co : (const bf16*)p.dz, pred);
+                    cp_async16(sA + ((mn8 * KC) + wpp) * 16, pred ? (const bf16*)p.dz + pos * p.Cout + co : (const bf16*)p.dz, pred);
                 }
                 int wo = 0, ho = 0, n = 0;
                 if (pos_ok && !is1x1) {
                     wo = (int)(pos % p.Wo); ho = (int)((pos / p.Wo) % p.Ho); n = (int)(pos / ((long long)p.Wo * p.Ho));
                 }
                 const int nmn = BN >> 3;
-                int b = 0;
-                for (int mn8 = half; mn8 < nmn; mn8 += 2, ++b) {   // B = a^T
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {      // B = a^T
+                    const int mn8 = wq + 4 * b;
+                    if (mn8 >= nmn) continue;
                     const int kk = it.n0 + mn8 * 8;
                     const bf16* src = (const bf16*)p.x;
                     bool pred = pos_ok && kk < Ntot;
@@ -340,47 +351,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                         if (is1x1) src += pos * p.Cin + kk;
                         else {
                             const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
-                            const int kh = tap / p.k, kw = tap - kh * p.k;
+                            const int kh = tap / 3, kw = tap - kh * 3;
                             const int ih = ho * p.stride - p.pad + kh, iw = wo * p.stride - p.pad + kw;
                             pred = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
                             if (pred) src += (((long long)n * p.H + ih) * p.W + iw) * p.Cin + ci;
                         }
                     }
-                    cp_async16(sB + ((mn8 * KC) + pp) * 16, src, pred);
+                    cp_async16(sB + ((mn8 * KC) + wpp) * 16, src, pred);
                     mask |= (pred ? 1u : 0u) << b;
                 }
             }
-            s_mask[it.stage * 128 + tid] = (unsigned char)mask;
+            s_mask[it.stage * 256 + tid] = (unsigned char)mask;
             cp_async_commit();
         };
-        // ---- finish: BN-apply + ReLU in place on the vectors this thread copied, then publish the stage ----
+        // ---- finish: BN-apply + ReLU in place on the vectors this thread copied (loads first: ILP), publish ----
         auto finish = [&](ChunkIt& it) {
             if (xf) {
                 unsigned char* sA = sStage + it.stage * g.stage_bytes;
-                unsigned mask = s_mask[it.stage * 128 + tid];
+                const unsigned mask = s_mask[it.stage * 256 + tid];
                 const long long k0 = it.c * kc;
-                if (MODE == MODE_FWD) {
-                    int cc = is1x1 ? (int)k0 : (int)(k0 % p.Cin);
-                    for (int k8 = 0; mask; ++k8, mask >>= 1) {
-                        if (mask & 1u) {
-                            uint4* q = reinterpret_cast<uint4*>(sA + ((k8 * 128) + tid) * 16);
-                            *q = xform8(*q, s_scale, s_shift, cc);
-                        }
-                        cc += 8;
-                        if (cc >= p.Cin) cc -= p.Cin;
+                uint4 q[4];
+                int cch[4];
+                uint4* ptr[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (MODE == MODE_FWD) {
+                        const int k8 = 2 * i + ppar;
+                        const long long kk = k0 + k8 * 8;
+                        cch[i] = is1x1 ? (int)kk : (int)(kk % p.Cin);
+                        ptr[i] = reinterpret_cast<uint4*>(sA + ((k8 * 128) + prow) * 16);
+                    } else {
+                        const int mn8 = wq + 4 * i;
+                        const int kk = it.n0 + mn8 * 8;
+                        cch[i] = is1x1 ? kk : kk % p.Cin;
+                        ptr[i] = reinterpret_cast<uint4*>(sA + 128 * KC * 2 + ((mn8 * KC) + wpp) * 16);
                     }
-                } else if (MODE == MODE_WGRAD) {
-                    unsigned char* sB = sA + 128 * KC * 2;
-                    const int pp = tid & 63, half = tid >> 6;
-                    for (int mn8 = half; mask; mn8 += 2, mask >>= 1) {
-                        if (mask & 1u) {
-                            const int kk = it.n0 + mn8 * 8;
-                            const int ci = is1x1 ? kk : kk % p.Cin;
-                            uint4* q = reinterpret_cast<uint4*>(sB + ((mn8 * KC) + pp) * 16);
-                            *q = xform8(*q, s_scale, s_shift, ci);
-                        }
-                    }
+                    if (mask & (1u << i)) q[i] = *ptr[i];
                 }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (mask & (1u << i)) *ptr[i] = xform8(q[i], s_scale, s_shift, cch[i]);
             }
             fence_async_proxy();
             mbar_arrive(&full[it.stage]);
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
         }
         cp_async_wait<0>();
         for (; pending > 0; --pending) { finish(fs); advance(fs); }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         // =========================== MMA ISSUER ===========================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
@@ -452,28 +462,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
         }
         __syncwarp();
     } else {
-        // =========================== EPILOGUE ===========================
-        const int et = tid - 128;                      // accumulator row owned by this thread
+        // =========================== EPILOGUE (two groups of 4 warps, alternating tiles) ===========================
+        const int grp = (warp - 8) >> 2;               // 0: warps 8-11, 1: warps 12-15 ; group g owns accumulator g
+        const int et = (tid - 256) & 127;              // accumulator row owned by this thread
         const int ew = et >> 5;                        // == warp % 4 : TMEM lanes 32*ew .. 32*ew+31
-        int a = 0;
+        unsigned char* sCg = sC + grp * c_bytes;
+        float* s_redg = s_red + grp * 256;
         uint32_t aph = 0;
-        float st[4] = {0.f, 0.f, 0.f, 0.f};
-        const int ncp = BN >> 1;
-        const int groups = 128 / ncp;
-        const int cpi = et % ncp, rg = et / ncp;
-        for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        // fused write-out + statistics pass: thread owns the 16-byte column vector c8o of rows rgo, rgo+groups, ...
+        const int vpr = BN >> 3;
+        const int groups = 128 / vpr;
+        const int c8o = et % vpr, rgo = et / vpr;
+        const bool pass_active = rgo < groups;
+        float sacc[8], qacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sacc[j] = qacc[j] = 0.f;
+        const bool do_stats = (MODE == MODE_FWD) && p.stats != nullptr;
+        long long local = 0;
+        for (long long unit = blockIdx.x; unit < units; unit += gridDim.x, ++local) {
+            if ((local & 1) != grp) continue;
             const int nt = (int)((unit / g.ksplit) % g.n_tiles);
             const long long mt = unit / ((long long)g.ksplit * g.n_tiles);
             const long long m0 = mt * 128;
             const int n0 = nt * BN;
-            mbar_wait(&acc_full[a], aph);
+            mbar_wait(&acc_full[grp], aph);
+            aph ^= 1;
             tc_fence_after();
             const long long row_g = m0 + et;
-            const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN);
+            const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(grp * BN);
             if (MODE == MODE_WGRAD) {
                 for (int c0 = 0; c0 < BN; c0 += 16) {
                     uint32_t r[16];
                     tmem_ld16(t_lane + c0, r);
+                    tmem_ld_wait();
                     if (row_g < Mtot) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -486,79 +507,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[a]);
+                mbar_arrive(&acc_empty[grp]);
             } else {
                 const int ldo = (MODE == MODE_FWD) ? p.Cout : p.Cin;
-                for (int c0 = 0; c0 < BN; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(t_lane + c0, r);
-                    float v[16];
+                for (int cb = 0; cb < BN; cb += 32) {          // batches of up to 32 columns: loads back to back, one wait
+                    uint32_t r[2][16];
+                    const int nb = (BN - cb) >= 32 ? 2 : 1;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                    if (MODE == MODE_FWD) {
+                    for (int q = 0; q < 2; ++q)
+                        if (q < nb) tmem_ld16(t_lane + cb + q * 16, r[q]);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += s_bias[c0 + j];
-                    } else if (p.add && row_g < Mtot) {
-                        const bf16* ap = (const bf16*)p.add + row_g * ldo + n0 + c0;
-                        if (n0 + c0 + 16 <= Ntot) {
-                            float a0[8], a1[8];
-                            load8(ap, a0);
-                            load8(ap + 8, a1);
+                    for (int q = 0; q < 2; ++q) {
+                        if (q >= nb) continue;
+                        const int c0 = cb + q * 16;
+                        float v[16];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
-                        } else {
-                            for (int j = 0; j < 16; ++j)
-                                if (n0 + c0 + j < Ntot) v[j] += to_f(ap[j]);
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[q][j]);
+                        if (MODE == MODE_FWD) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += s_bias[c0 + j];
+                        } else if (p.add && row_g < Mtot) {
+                            const bf16* ap = (const bf16*)p.add + row_g * ldo + n0 + c0;
+                            if (n0 + c0 + 16 <= Ntot) {
+                                float a0[8], a1[8];
+                                load8(ap, a0);
+                                load8(ap + 8, a1);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
+                            } else {
+                                for (int j = 0; j < 16; ++j)
+                                    if (n0 + c0 + j < Ntot) v[j] += to_f(ap[j]);
+                            }
                         }
-                    }
-                    float lo[8], hi[8];
+                        float lo[8], hi[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-                    unsigned char* dst = sC + et * c_pitch + c0 * 2;
-                    *reinterpret_cast<uint4*>(dst) = pack_bf16x8(lo);
-                    *reinterpret_cast<uint4*>(dst + 16) = pack_bf16x8(hi);
+                        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+                        unsigned char* dst = sCg + et * c_pitch + c0 * 2;
+                        *reinterpret_cast<uint4*>(dst) = pack_bf16x8(lo);
+                        *reinterpret_cast<uint4*>(dst + 16) = pack_bf16x8(hi);
+                    }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[a]);            // accumulator drained: the MMA warp may reuse it
-                named_bar_sync(1, 128);
-                // coalesced write-out of the staged tile
-                const int vpr = BN >> 3;
-                for (int vi = et; vi < 128 * vpr; vi += 128) {
-                    const int row = vi / vpr, c8 = vi - row * vpr;
-                    const long long mm = m0 + row;
-                    const int col = n0 + c8 * 8;
-                    if (mm < Mtot && col < Ntot)
-                        *reinterpret_cast<uint4*>((bf16*)p.out + mm * ldo + col) =
-                            *reinterpret_cast<const uint4*>(sC + row * c_pitch + c8 * 16);
-                }
-                if (MODE == MODE_FWD && p.stats && rg < groups) {
-                    // column-pair owner threads: sum / sum of squares of the STORED (bf16-rounded) values
+                mbar_arrive(&acc_empty[grp]);          // accumulator drained: the MMA warp may reuse it
+                named_bar_sync(1 + grp, 128);
+                if (pass_active) {
                     const int rows_here = (int)(Mtot - m0 < 128 ? Mtot - m0 : 128);
-                    for (int row = rg; row < rows_here; row += groups) {
-                        const uint32_t w2 = *reinterpret_cast<const uint32_t*>(sC + row * c_pitch + cpi * 4);
-                        const float x0 = __uint_as_float(w2 << 16), x1 = __uint_as_float(w2 & 0xffff0000u);
-                        st[0] += x0; st[1] += x1;
-                        st[2] = fmaf(x0, x0, st[2]); st[3] = fmaf(x1, x1, st[3]);
+                    const int col = n0 + c8o * 8;
+                    if (col < Ntot) {
+                        bf16* outp = (bf16*)p.out + m0 * ldo + col;
+                        const unsigned char* sp = sCg + c8o * 16;
+#pragma unroll 4
+                        for (int row = rgo; row < rows_here; row += groups) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(sp + row * c_pitch);
+                            *reinterpret_cast<uint4*>(outp + (long long)row * ldo) = q;
+                            if (do_stats) {
+                                float x[8];
+                                unpack_bf16x8(q, x);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { sacc[j] += x[j]; qacc[j] = fmaf(x[j], x[j], qacc[j]); }
+                            }
+                        }
                     }
                 }
-                named_bar_sync(1, 128);                // stage buffer free for the next tile
+                named_bar_sync(1 + grp, 128);          // stage buffer free for this group's next tile
             }
-            if (++a == 2) { a = 0; aph ^= 1; }
         }
-        if (MODE == MODE_FWD && p.stats) {
-            // the N tile is fixed per CTA: one flush at the end
-            for (int i = et; i < 2 * BN; i += 128) s_red[i] = 0.f;
-            named_bar_sync(1, 128);
-            if (rg < groups) {
-                atomicAdd(&s_red[cpi * 2], st[0]); atomicAdd(&s_red[cpi * 2 + 1], st[1]);
-                atomicAdd(&s_red[BN + cpi * 2], st[2]); atomicAdd(&s_red[BN + cpi * 2 + 1], st[3]);
+        if (do_stats) {
+            // the N tile is fixed per CTA: one flush per group at the end
+            for (int i = et; i < 2 * BN; i += 128) s_redg[i] = 0.f;
+            named_bar_sync(1 + grp, 128);
+            if (pass_active) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    atomicAdd(&s_redg[c8o * 8 + j], sacc[j]);
+                    atomicAdd(&s_redg[BN + c8o * 8 + j], qacc[j]);
+                }
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(1 + grp, 128);
             const int n0 = nt_fixed * BN;
             for (int i = et; i < BN; i += 128)
                 if (n0 + i < Ntot) {
-                    atomicAdd(&p.stats[n0 + i], (double)s_red[i]);
-                    atomicAdd(&p.stats[p.Cout + n0 + i], (double)s_red[BN + i]);
+                    atomicAdd(&p.stats[n0 + i], (double)s_redg[i]);
+                    atomicAdd(&p.stats[p.Cout + n0 + i], (double)s_redg[BN + i]);
                 }
         }
     }
@@ -595,8 +626,8 @@ static bool tc_geom(int mode, const ConvP& p, TcGeom& g, size_t& smem, int& dept
     g.stage_bytes = 128 * g.kc * 2 + ((mode == MODE_WGRAD || !g.b_resident) ? BN * g.kc * 2 : 0);
     const int xch = mode == MODE_DGRAD ? 0 : p.Cin;
     const size_t fixed = (g.b_resident ? (size_t)BN * g.kpad * 2 : 0) +
-                         (mode == MODE_WGRAD ? 0 : (size_t)128 * (BN * 2 + 16)) + (size_t)2 * xch * 4 + (128 + 256) * 4 +
-                         (2 * MAXSTAGE + 4) * 8 + 16 + MAXSTAGE * 128 + 128;
+                         (mode == MODE_WGRAD ? 0 : (size_t)2 * 128 * (BN * 2 + 16)) + (size_t)2 * xch * 4 + (128 + 512) * 4 +
+                         (2 * MAXSTAGE + 4) * 8 + 16 + MAXSTAGE * 256 + 128;
     // deep ring of small stages when the chunk is small (memory-level parallelism), else 5 x up to 32 KB
     depth = ((size_t)10 * g.stage_bytes + fixed <= 220 * 1024) ? 8 : 3;
     g.nstage = depth + 2;
