@@ -245,6 +245,13 @@ static int launch_dw_wgrad(const T* x, const float* s, const float* t, const T* 
     return 0;
 }
 
+// shared-memory halo-tile kernels (dwconv_tile.cu), bf16 only
+int dw_fwd_tile(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z, double* stats,
+                int N, int H, int W, int C, int k, cudaStream_t st);
+int dw_dgrad_tile(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
+int dw_wgrad_tile(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C,
+                  int k, cudaStream_t st);
+
 static int check_dw(const char* name, int N, int H, int W, int C, int k, int dtype) {
     MNB_REQUIRE(N > 0 && H > 0 && W > 0, "%s: bad N/H/W", name);
     MNB_REQUIRE(C > 0 && C % 8 == 0, "%s: C=%d must be a positive multiple of 8", name, C);
@@ -263,6 +270,10 @@ int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, cons
                void* z, double* stats, int N, int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_fwd", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_BF16) {
+        int r = dw_fwd_tile(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_F32) {
         if (k == 3) launch_dw_fwd<float, 3, false>((const float*)x, in_scale, in_shift, w, bias, (float*)z, stats, N, H, W, C, st);
         else launch_dw_fwd<float, 5, false>((const float*)x, in_scale, in_shift, w, bias, (float*)z, stats, N, H, W, C, st);
@@ -278,6 +289,10 @@ int mnb_dw_dgrad(const void* dz, const float* w, void* dx, int N, int H, int W, 
                  void* stream) {
     if (int e = check_dw("dw_dgrad", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_BF16) {
+        int r = dw_dgrad_tile(dz, w, dx, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_F32) {
         if (k == 3) launch_dw_fwd<float, 3, true>((const float*)dz, nullptr, nullptr, w, nullptr, (float*)dx, nullptr, N, H, W, C, st);
         else launch_dw_fwd<float, 5, true>((const float*)dz, nullptr, nullptr, w, nullptr, (float*)dx, nullptr, N, H, W, C, st);
@@ -293,6 +308,10 @@ int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, co
                  int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_wgrad", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_BF16) {
+        int r = dw_wgrad_tile(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_F32) {
         if (k == 3) launch_dw_wgrad<float, 3>((const float*)x, in_scale, in_shift, (const float*)dz, dw, N, H, W, C, st);
         else launch_dw_wgrad<float, 5>((const float*)x, in_scale, in_shift, (const float*)dz, dw, N, H, W, C, st);
