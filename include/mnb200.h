@@ -50,8 +50,12 @@ int mnb_device_is_sm100(void);
 int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                  void* z, double* stats, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                  int dtype, int x_layout, int impl, void* stream);
-/* dx[n,h,w,ci] = (add ? add[n,h,w,ci] : 0) + sum dz[n,ho,wo,co]*w[co,ci,kh,kw]   (conv backward-data) */
-int mnb_conv_dgrad(const void* dz, const float* w, const void* add, void* dx, int N, int H, int W, int Cin,
+/* dx[n,h,w,ci] = (add ? add[n,h,w,ci] : 0) + sum dz[n,ho,wo,co]*w[co,ci,kh,kw]   (conv backward-data)
+ * Optional fused BatchNorm-backward reduction for the ConvBlock that PRODUCED this conv's input (dx is its dA):
+ * when bn_z != NULL, bn_sums[0:Cin] += sum G and bn_sums[Cin:2Cin] += sum G*z with
+ * G = dx * [bn_scale*z + bn_shift > 0], z = bn_z (same shape as dx) -- i.e. what mnb_bn_bwd_reduce computes. */
+int mnb_conv_dgrad(const void* dz, const float* w, const void* add, void* dx, const void* bn_z,
+                   const float* bn_scale, const float* bn_shift, double* bn_sums, int N, int H, int W, int Cin,
                    int Cout, int k, int stride, int pad, int dtype, int impl, void* stream);
 /* dw[co,ci,kh,kw] += sum a(...)*dz[...]  (conv backward-weight; fp32 accumulate INTO dw) */
 int mnb_conv_wgrad(const void* x, const float* in_scale, const float* in_shift, const void* dz, float* dw,
@@ -62,7 +66,9 @@ int mnb_conv_wgrad(const void* x, const float* in_scale, const float* in_shift, 
 int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w /*[C,1,k,k]*/,
                const float* bias, void* z, double* stats, int N, int H, int W, int C, int k, int dtype,
                void* stream);
-int mnb_dw_dgrad(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, int dtype,
+/* bn_z/bn_scale/bn_shift/bn_sums: optional fused BN-backward reduction, see mnb_conv_dgrad */
+int mnb_dw_dgrad(const void* dz, const float* w, void* dx, const void* bn_z, const float* bn_scale,
+                 const float* bn_shift, double* bn_sums, int N, int H, int W, int C, int k, int dtype,
                  void* stream);
 int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, const void* dz, float* dw,
                  int N, int H, int W, int C, int k, int dtype, void* stream);

@@ -16,7 +16,10 @@ struct ConvP {
     const void* add;      // dgrad residual
     void* out;            // fwd: z; dgrad: dx
     float* dw;            // wgrad
-    double* stats;
+    double* stats;        // fwd: BN statistics of z; dgrad: fused BN-backward sums of the producer block
+    const void* bn_z;     // dgrad: raw conv output of the producer block (NULL = no fused reduction)
+    const float* bn_scale;
+    const float* bn_shift;
     int N, H, W, Cin, Ho, Wo, Cout, k, stride, pad;
     int nchw_in;          // x is NCHW fp32
     long long kchunk;     // wgrad: positions per blockIdx.z

@@ -225,6 +225,8 @@ __global__ void __launch_bounds__(256) conv_simt_k(ConvP p) {
     } else if (MODE == MODE_DGRAD) {
         T* dx = (T*)p.out;
         const T* add = (const T*)p.add;
+        const T* bz = (const T*)p.bn_z;
+        float cs[4] = {0, 0, 0, 0}, cq[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             long long m = m0 + ty * 4 + i;
@@ -235,7 +237,28 @@ __global__ void __launch_bounds__(256) conv_simt_k(ConvP p) {
                 if (ci >= Ntot) continue;
                 float v = acc[i][j];
                 if (add) v += to_f(add[m * p.Cin + ci]);
-                dx[m * p.Cin + ci] = from_f<T>(v);
+                T q = from_f<T>(v);
+                dx[m * p.Cin + ci] = q;
+                if (bz) {       // fused BN-backward reduction of the producer block
+                    const float zz = to_f(bz[m * p.Cin + ci]);
+                    const float g = fmaf(p.bn_scale[ci], zz, p.bn_shift[ci]) > 0.f ? to_f(q) : 0.f;
+                    cs[j] += g;
+                    cq[j] = fmaf(g, zz, cq[j]);
+                }
+            }
+        }
+        if (bz && p.stats) {
+            if (tid < 128) (&sred[0][0])[tid] = 0.f;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&sred[0][tx * 4 + j], cs[j]);
+                atomicAdd(&sred[1][tx * 4 + j], cq[j]);
+            }
+            __syncthreads();
+            if (tid < 64 && n0 + tid < Ntot) {
+                atomicAdd(&p.stats[n0 + tid], (double)sred[0][tid]);
+                atomicAdd(&p.stats[p.Cin + n0 + tid], (double)sred[1][tid]);
             }
         }
     } else {
@@ -253,6 +276,12 @@ __global__ void __launch_bounds__(256) conv_simt_k(ConvP p) {
         }
     }
 }
+
+// dedicated stem kernels (stem.cu)
+bool stem_supported(int Cin, int Cout, int k, int stride, int pad, int nchw_in);
+int stem_fwd(const float* x, const float* w, const float* bias, void* z, double* stats, int N, int H, int W, int dtype,
+             cudaStream_t st);
+int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, int dtype, cudaStream_t st);
 
 static int check_conv(const char* name, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dtype,
                       int x_layout) {
@@ -312,6 +341,8 @@ int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, co
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
     p.nchw_in = x_layout == MNB_LAYOUT_NCHW_F32;
+    if (impl != 1 && in_scale == nullptr && stem_supported(Cin, Cout, k, stride, pad, p.nchw_in))
+        return stem_fwd((const float*)x, w, bias, z, stats, N, H, W, dtype, (cudaStream_t)stream);
     if (impl != 1 && dtype == MNB_BF16) {
         int r = conv_fwd_tc(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -320,11 +351,14 @@ int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, co
     return conv_fwd_simt(p, dtype, (cudaStream_t)stream);
 }
 
-int mnb_conv_dgrad(const void* dz, const float* w, const void* add, void* dx, int N, int H, int W, int Cin, int Cout,
-                   int k, int stride, int pad, int dtype, int impl, void* stream) {
+int mnb_conv_dgrad(const void* dz, const float* w, const void* add, void* dx, const void* bn_z, const float* bn_scale,
+                   const float* bn_shift, double* bn_sums, int N, int H, int W, int Cin, int Cout, int k, int stride,
+                   int pad, int dtype, int impl, void* stream) {
     if (int e = check_conv("conv_dgrad", N, H, W, Cin, Cout, k, stride, pad, dtype, MNB_LAYOUT_NHWC)) return e;
+    MNB_REQUIRE(!bn_z || (bn_scale && bn_shift && bn_sums), "conv_dgrad: bn_z needs bn_scale/bn_shift/bn_sums");
     ConvP p = {};
     p.dz = dz; p.w = w; p.add = add; p.out = dx;
+    p.bn_z = bn_z; p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.stats = bn_z ? bn_sums : nullptr;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
     if (impl != 1 && dtype == MNB_BF16) {
@@ -344,6 +378,8 @@ int mnb_conv_wgrad(const void* x, const float* in_scale, const float* in_shift, 
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
     p.nchw_in = x_layout == MNB_LAYOUT_NCHW_F32;
+    if (impl != 1 && in_scale == nullptr && stem_supported(Cin, Cout, k, stride, pad, p.nchw_in))
+        return stem_wgrad((const float*)x, dz, dw, N, H, W, dtype, (cudaStream_t)stream);
     if (impl != 1 && dtype == MNB_BF16) {
         int r = conv_wgrad_tc(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;

@@ -41,10 +41,13 @@ template <typename T, int K, int TH, int TW, bool XF, bool FLIP, bool STATS>
 __global__ void __launch_bounds__(128) dw_fwd_k(const T* __restrict__ x, const float* __restrict__ in_scale,
                                                 const float* __restrict__ in_shift, const float* __restrict__ w,
                                                 const float* __restrict__ bias, T* __restrict__ z, double* stats,
-                                                int N, int H, int W, int C) {
+                                                const T* __restrict__ bnz, const float* __restrict__ bns,
+                                                const float* __restrict__ bnt, int N, int H, int W, int C) {
     constexpr int P = K / 2;
     constexpr int IW = TW + K - 1;
     const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    float gs0 = 0.f, gs1 = 0.f, gt0 = 0.f, gt1 = 0.f;       // dgrad: producer block's BN scale/shift
+    if (FLIP && STATS) { gs0 = bns[c0]; gs1 = bns[c0 + 1]; gt0 = bnt[c0]; gt1 = bnt[c0 + 1]; }
     float wr[K][K][2];
 #pragma unroll
     for (int i = 0; i < K; ++i)
@@ -114,8 +117,16 @@ __global__ void __launch_bounds__(128) dw_fwd_k(const T* __restrict__ x, const f
                         if (STATS) {
                             // statistics of the values as stored (bf16-rounded in bf16 mode)
                             float q0 = to_f(from_f<T>(v0)), q1 = to_f(from_f<T>(v1));
-                            st[0] += q0; st[1] += q1;
-                            st[2] = fmaf(q0, q0, st[2]); st[3] = fmaf(q1, q1, st[3]);
+                            if (!FLIP) {
+                                st[0] += q0; st[1] += q1;
+                                st[2] = fmaf(q0, q0, st[2]); st[3] = fmaf(q1, q1, st[3]);
+                            } else {    // fused BN-backward reduction of the producer block
+                                const float2 zz = load2(bnz + (long long)n * H * W * C + c0 + ((long long)oh * W + w0 + j) * C);
+                                const float g0 = fmaf(gs0, zz.x, gt0) > 0.f ? q0 : 0.f;
+                                const float g1 = fmaf(gs1, zz.y, gt1) > 0.f ? q1 : 0.f;
+                                st[0] += g0; st[1] += g1;
+                                st[2] = fmaf(g0, zz.x, st[2]); st[3] = fmaf(g1, zz.y, st[3]);
+                            }
                         }
                     }
                 }
@@ -225,13 +236,14 @@ __global__ void __launch_bounds__(128) dw_wgrad_k(const T* __restrict__ x, const
 
 template <typename T, int K, bool FLIP>
 static int launch_dw_fwd(const T* x, const float* s, const float* t, const float* w, const float* bias, T* z,
-                         double* stats, int N, int H, int W, int C, cudaStream_t st) {
+                         double* stats, const T* bnz, const float* bns, const float* bnt, int N, int H, int W, int C,
+                         cudaStream_t st) {
     constexpr int TH = 8, TW = 4;
     DwGeom g = dw_geom<TH, TW>(N, H, W, C, 8);
-    if (s && stats) dw_fwd_k<T, K, TH, TW, true, FLIP, true><<<g.grid, g.block, 0, st>>>(x, s, t, w, bias, z, stats, N, H, W, C);
-    else if (s) dw_fwd_k<T, K, TH, TW, true, FLIP, false><<<g.grid, g.block, 0, st>>>(x, s, t, w, bias, z, stats, N, H, W, C);
-    else if (stats) dw_fwd_k<T, K, TH, TW, false, FLIP, true><<<g.grid, g.block, 0, st>>>(x, s, t, w, bias, z, stats, N, H, W, C);
-    else dw_fwd_k<T, K, TH, TW, false, FLIP, false><<<g.grid, g.block, 0, st>>>(x, s, t, w, bias, z, stats, N, H, W, C);
+    if (s && stats) dw_fwd_k<T, K, TH, TW, true, FLIP, true><<<g.grid, g.block, 0, st>>>(x, s, t, w, bias, z, stats, bnz, bns, bnt, N, H, W, C);
+    else if (s) dw_fwd_k<T, K, TH, TW, true, FLIP, false><<<g.grid, g.block, 0, st>>>(x, s, t, w, bias, z, stats, bnz, bns, bnt, N, H, W, C);
+    else if (stats) dw_fwd_k<T, K, TH, TW, false, FLIP, true><<<g.grid, g.block, 0, st>>>(x, s, t, w, bias, z, stats, bnz, bns, bnt, N, H, W, C);
+    else dw_fwd_k<T, K, TH, TW, false, FLIP, false><<<g.grid, g.block, 0, st>>>(x, s, t, w, bias, z, stats, bnz, bns, bnt, N, H, W, C);
     return 0;
 }
 
@@ -248,7 +260,8 @@ static int launch_dw_wgrad(const T* x, const float* s, const float* t, const T* 
 // shared-memory halo-tile kernels (dwconv_tile.cu), bf16 only
 int dw_fwd_tile(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z, double* stats,
                 int N, int H, int W, int C, int k, cudaStream_t st);
-int dw_dgrad_tile(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
+int dw_dgrad_tile(const void* dz, const float* w, void* dx, const void* bn_z, const float* bn_scale,
+                  const float* bn_shift, double* bn_sums, int N, int H, int W, int C, int k, cudaStream_t st);
 int dw_wgrad_tile(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C,
                   int k, cudaStream_t st);
 
@@ -275,30 +288,32 @@ int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, cons
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
     if (dtype == MNB_F32) {
-        if (k == 3) launch_dw_fwd<float, 3, false>((const float*)x, in_scale, in_shift, w, bias, (float*)z, stats, N, H, W, C, st);
-        else launch_dw_fwd<float, 5, false>((const float*)x, in_scale, in_shift, w, bias, (float*)z, stats, N, H, W, C, st);
+        if (k == 3) launch_dw_fwd<float, 3, false>((const float*)x, in_scale, in_shift, w, bias, (float*)z, stats, nullptr, nullptr, nullptr, N, H, W, C, st);
+        else launch_dw_fwd<float, 5, false>((const float*)x, in_scale, in_shift, w, bias, (float*)z, stats, nullptr, nullptr, nullptr, N, H, W, C, st);
     } else {
-        if (k == 3) launch_dw_fwd<bf16, 3, false>((const bf16*)x, in_scale, in_shift, w, bias, (bf16*)z, stats, N, H, W, C, st);
-        else launch_dw_fwd<bf16, 5, false>((const bf16*)x, in_scale, in_shift, w, bias, (bf16*)z, stats, N, H, W, C, st);
+        if (k == 3) launch_dw_fwd<bf16, 3, false>((const bf16*)x, in_scale, in_shift, w, bias, (bf16*)z, stats, nullptr, nullptr, nullptr, N, H, W, C, st);
+        else launch_dw_fwd<bf16, 5, false>((const bf16*)x, in_scale, in_shift, w, bias, (bf16*)z, stats, nullptr, nullptr, nullptr, N, H, W, C, st);
     }
     MNB_LAUNCH_CHECK("dw_fwd");
     return 0;
 }
 
-int mnb_dw_dgrad(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, int dtype,
-                 void* stream) {
+int mnb_dw_dgrad(const void* dz, const float* w, void* dx, const void* bn_z, const float* bn_scale,
+                 const float* bn_shift, double* bn_sums, int N, int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_dgrad", N, H, W, C, k, dtype)) return e;
+    MNB_REQUIRE(!bn_z || (bn_scale && bn_shift && bn_sums), "dw_dgrad: bn_z needs bn_scale/bn_shift/bn_sums");
+    if (!bn_z) bn_sums = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MNB_BF16) {
-        int r = dw_dgrad_tile(dz, w, dx, N, H, W, C, k, st);
+        int r = dw_dgrad_tile(dz, w, dx, bn_z, bn_scale, bn_shift, bn_sums, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
     if (dtype == MNB_F32) {
-        if (k == 3) launch_dw_fwd<float, 3, true>((const float*)dz, nullptr, nullptr, w, nullptr, (float*)dx, nullptr, N, H, W, C, st);
-        else launch_dw_fwd<float, 5, true>((const float*)dz, nullptr, nullptr, w, nullptr, (float*)dx, nullptr, N, H, W, C, st);
+        if (k == 3) launch_dw_fwd<float, 3, true>((const float*)dz, nullptr, nullptr, w, nullptr, (float*)dx, bn_sums, (const float*)bn_z, bn_scale, bn_shift, N, H, W, C, st);
+        else launch_dw_fwd<float, 5, true>((const float*)dz, nullptr, nullptr, w, nullptr, (float*)dx, bn_sums, (const float*)bn_z, bn_scale, bn_shift, N, H, W, C, st);
     } else {
-        if (k == 3) launch_dw_fwd<bf16, 3, true>((const bf16*)dz, nullptr, nullptr, w, nullptr, (bf16*)dx, nullptr, N, H, W, C, st);
-        else launch_dw_fwd<bf16, 5, true>((const bf16*)dz, nullptr, nullptr, w, nullptr, (bf16*)dx, nullptr, N, H, W, C, st);
+        if (k == 3) launch_dw_fwd<bf16, 3, true>((const bf16*)dz, nullptr, nullptr, w, nullptr, (bf16*)dx, bn_sums, (const bf16*)bn_z, bn_scale, bn_shift, N, H, W, C, st);
+        else launch_dw_fwd<bf16, 5, true>((const bf16*)dz, nullptr, nullptr, w, nullptr, (bf16*)dx, bn_sums, (const bf16*)bn_z, bn_scale, bn_shift, N, H, W, C, st);
     }
     MNB_LAUNCH_CHECK("dw_dgrad");
     return 0;

@@ -53,7 +53,10 @@ struct DwP {
     const bf16* dz;         // wgrad
     bf16* out;              // fwd: z ; dgrad: dx
     float* dw;              // wgrad
-    double* stats;
+    double* stats;          // fwd: BN statistics ; dgrad: fused BN-backward sums of the producer block
+    const bf16* bn_z;       // dgrad: producer block's raw conv output (NULL = no fused reduction)
+    const float* bn_scale;
+    const float* bn_shift;
     int N, H, W, C;
     int tiles_h, tiles_w;
     long long items;        // N * tiles_h * tiles_w
@@ -91,13 +94,16 @@ __device__ __forceinline__ uint4 dw_xform8(uint4 u, const float* s, const float*
 }
 
 // MODE 0: forward (XF optional, bias, stats)   MODE 1: dgrad (flipped kernel, plain input)   MODE 2: wgrad
+// MODE 3: dgrad + fused BN-backward reduction of the producer block (second, halo-free tile holds its z)
 template <int K, int CB, int MODE>
 __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
     using Cfg = DwCfg<K, CB>;
     constexpr int P = Cfg::P, NP = Cfg::NP, CW = Cfg::CW, WX = Cfg::WX, TH = Cfg::TH, HC = Cfg::HC, HR = Cfg::HR;
     constexpr int CV8 = Cfg::CV8, NV = Cfg::NV, MAXV = Cfg::MAXV, THT = Cfg::THT, TW = Cfg::TW, PP = Cfg::PP;
     extern __shared__ __align__(128) unsigned char dsm[];
-    constexpr int STAGE = Cfg::TILE_BYTES + (MODE == 2 ? Cfg::DZ_BYTES : 0);
+    constexpr bool SIDE = (MODE == 2 || MODE == 3);  // wgrad: dz tile; fused dgrad: bn_z tile
+    constexpr bool DGRAD = (MODE == 1 || MODE == 3);
+    constexpr int STAGE = Cfg::TILE_BYTES + (SIDE ? Cfg::DZ_BYTES : 0);
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int cbase = blockIdx.y * CB;
     const int cp = lane % NP, csub = lane / NP;
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
     const int c0 = (wx * CW + csub) * 2;            // first of the 2 tile-local output columns of this thread
     const int r0 = wy * TH;                         // first tile-local output row
     const int ch = cbase + cp * 2;                  // global channel of the pair
-    const bool xf = (MODE != 1) && p.in_scale != nullptr;
+    const bool xf = !DGRAD && p.in_scale != nullptr;
 
     // per-thread constants
     f2_t wr[K][K];
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
         for (int i = 0; i < K; ++i)
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                const int ii = MODE == 1 ? K - 1 - i : i, jj = MODE == 1 ? K - 1 - j : j;
+                const int ii = DGRAD ? K - 1 - i : i, jj = DGRAD ? K - 1 - j : j;
                 wr[i][j] = f2_pack(lane_on ? p.w[(ch + 0) * K * K + ii * K + jj] : 0.f,
                                    lane_on ? p.w[(ch + 1) * K * K + ii * K + jj] : 0.f);
             }
@@ -128,6 +134,9 @@ __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
     float b0 = 0.f, b1 = 0.f;
     if (MODE == 0 && p.bias && lane_on) { b0 = p.bias[ch]; b1 = p.bias[ch + 1]; }
     float st[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool bn_red = (MODE == 3);
+    float gs0 = 0.f, gs1 = 0.f, gt0 = 0.f, gt1 = 0.f;
+    if (bn_red && lane_on) { gs0 = p.bn_scale[ch]; gs1 = p.bn_scale[ch + 1]; gt0 = p.bn_shift[ch]; gt1 = p.bn_shift[ch + 1]; }
 
     // ---- tile loader.  The decomposition of this thread's vector slots v = tid + i*256 -> (halo row, halo col,
     //      8-channel group) does not depend on the tile: do the divisions once, outside the tile loop. ----
@@ -141,7 +150,8 @@ __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
         s_rc[i] = (r << 16) | (c << 8) | cv;
     }
     int d_off[Cfg::MAXVD], d_rc[Cfg::MAXVD];
-    if (MODE == 2) {
+    const bf16* side = MODE == 2 ? p.dz : p.bn_z;      // second (halo-free) tile: dz for wgrad, bn_z for fused dgrad
+    if (SIDE) {
 #pragma unroll
         for (int i = 0; i < Cfg::MAXVD; ++i) {
             const int v = tid + i * 256;
@@ -174,15 +184,15 @@ __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
                 mask |= (pred ? 1u : 0u) << i;
             }
         }
-        if (MODE == 2) {
+        if (SIDE) {
             unsigned char* dzt = tile + Cfg::TILE_BYTES;
-            const bf16* dn = p.dz + (long long)n * p.H * p.W * p.C + cbase;
+            const bf16* dn = side + (long long)n * p.H * p.W * p.C + cbase;
 #pragma unroll
             for (int i = 0; i < Cfg::MAXVD; ++i) {
                 if (d_off[i] >= 0) {
                     const int oh = th_i * THT + (d_rc[i] >> 16), ow = tw_i * TW + ((d_rc[i] >> 8) & 0xff), cv = d_rc[i] & 0xff;
                     const bool pred = oh < p.H && ow < p.W;
-                    dcp_async16(dzt + d_off[i], pred ? dn + (long long)(oh * p.W + ow) * p.C + cv * 8 : p.dz, pred);
+                    dcp_async16(dzt + d_off[i], pred ? dn + (long long)(oh * p.W + ow) * p.C + cv * 8 : side, pred);
                 }
             }
         }
@@ -268,6 +278,16 @@ __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
                                     const float q0 = __uint_as_float(pk << 16), q1 = __uint_as_float(pk & 0xffff0000u);
                                     st[0] += q0; st[1] += q1;
                                     st[2] = fmaf(q0, q0, st[2]); st[3] = fmaf(q1, q1, st[3]);
+                                } else if (bn_red) {
+                                    // fused BN-backward reduction of the producer block: G = dx*[s*z+t>0]
+                                    const float q0 = __uint_as_float(pk << 16), q1 = __uint_as_float(pk & 0xffff0000u);
+                                    const uint32_t zu = *reinterpret_cast<const uint32_t*>(
+                                        tile + Cfg::TILE_BYTES + ((r0 + od) * TW + c0 + tc) * PP + cp * 4);
+                                    const float z0 = __uint_as_float(zu << 16), z1 = __uint_as_float(zu & 0xffff0000u);
+                                    const float g0 = fmaf(gs0, z0, gt0) > 0.f ? q0 : 0.f;
+                                    const float g1 = fmaf(gs1, z1, gt1) > 0.f ? q1 : 0.f;
+                                    st[0] += g0; st[1] += g1;
+                                    st[2] = fmaf(g0, z0, st[2]); st[3] = fmaf(g1, z1, st[3]);
                                 }
                             }
                         }
@@ -309,7 +329,7 @@ __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
 
     // ---- per-CTA flush ----
     float* red = reinterpret_cast<float*>(dsm);     // reuse the (now idle) tile memory
-    if (MODE == 0 && p.stats) {
+    if ((MODE == 0 && p.stats) || bn_red) {
         for (int i = tid; i < 4 * NP; i += 256) red[i] = 0.f;
         __syncthreads();
         if (lane_on) {
@@ -346,7 +366,7 @@ __global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
 template <int K, int CB, int MODE>
 static int launch_dw_tile(DwP p, cudaStream_t st, const char* name) {
     using Cfg = DwCfg<K, CB>;
-    constexpr int STAGE = Cfg::TILE_BYTES + (MODE == 2 ? Cfg::DZ_BYTES : 0);
+    constexpr int STAGE = Cfg::TILE_BYTES + ((MODE == 2 || MODE == 3) ? Cfg::DZ_BYTES : 0);
     const int smem = 2 * STAGE;
     static bool attr_done = false;
     if (!attr_done) {
@@ -397,10 +417,13 @@ int dw_fwd_tile(const void* x, const float* s, const float* t, const float* w, c
     p.N = N; p.H = H; p.W = W; p.C = C;
     return dispatch_dw_tile<0>(p, k, st, "dw_fwd(tile)");
 }
-int dw_dgrad_tile(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st) {
+int dw_dgrad_tile(const void* dz, const float* w, void* dx, const void* bn_z, const float* bn_scale,
+                  const float* bn_shift, double* bn_sums, int N, int H, int W, int C, int k, cudaStream_t st) {
     DwP p = {};
     p.x = (const bf16*)dz; p.w = w; p.out = (bf16*)dx;
+    p.bn_z = (const bf16*)bn_z; p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.stats = bn_z ? bn_sums : nullptr;
     p.N = N; p.H = H; p.W = W; p.C = C;
+    if (p.bn_z && p.stats) return dispatch_dw_tile<3>(p, k, st, "dw_dgrad+bn(tile)");
     return dispatch_dw_tile<1>(p, k, st, "dw_dgrad(tile)");
 }
 int dw_wgrad_tile(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C,

@@ -37,24 +37,33 @@ static ColGeom col_geom(long long M, int C, int ctas_per_sm = 8) {
     return g;
 }
 
-// block-level reduction of per-thread 8-channel partials (threads sharing threadIdx.x) + fp64 atomic flush
+// block-level reduction of per-thread 8-channel partials (threads sharing threadIdx.x): shared-memory tree over
+// threadIdx.y (no atomics: with narrow tensors 128 threads share one channel vector), then one fp64 atomic per
+// channel per CTA
 template <int NQ>
 __device__ __forceinline__ void flush_channel_partials(float (&acc)[NQ][8], double* out, int C, int c0) {
-    __shared__ float red[NQ][32 * 8];
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int nt = blockDim.x * blockDim.y;
-    for (int i = tid; i < NQ * 32 * 8; i += nt) (&red[0][0])[i] = 0.f;
-    __syncthreads();
+    __shared__ float part[256 * NQ * 8];
+    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+    float* mine = part + (ty * TX + tx) * (NQ * 8);
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&red[q][threadIdx.x * 8 + i], acc[q][i]);
-    __syncthreads();
-    if (threadIdx.y == 0) {
+        for (int i = 0; i < 8; ++i) mine[q * 8 + i] = acc[q][i];
+    int s = 1;
+    while (s < TY) s <<= 1;
+    for (s >>= 1; s > 0; s >>= 1) {
+        __syncthreads();
+        if (ty < s && ty + s < TY) {
+            const float* other = part + ((ty + s) * TX + tx) * (NQ * 8);
+#pragma unroll
+            for (int k = 0; k < NQ * 8; ++k) mine[k] += other[k];
+        }
+    }
+    if (ty == 0) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(&out[q * C + c0 + i], (double)red[q][threadIdx.x * 8 + i]);
+            for (int i = 0; i < 8; ++i) atomicAdd(&out[q * C + c0 + i], (double)mine[q * 8 + i]);
     }
 }
 
@@ -100,21 +109,23 @@ template <typename T, bool RES>
 __global__ void __launch_bounds__(256) bn_relu_apply_k(const T* __restrict__ z, const float* __restrict__ scale,
                                                        const float* __restrict__ shift,
                                                        const T* __restrict__ res, T* __restrict__ y,
-                                                       long long nvec, int cv) {
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
-         v += (long long)gridDim.x * blockDim.x) {
-        int c0 = (int)(v % cv) * 8;
-        float a[8], r[8], s[8], t[8];
-        load8(z + v * 8, a);
-        load8(scale + c0, s);
-        load8(shift + c0, t);
-        if (RES) load8(res + v * 8, r);
+                                                       long long M, int C) {
+    // channel-owner threads: the per-channel constants stay in registers for the whole row loop
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    float s[8], t[8];
+    load8(scale + c0, s);
+    load8(shift + c0, t);
+    const long long stride = (long long)gridDim.y * blockDim.y;
+    for (long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += stride) {
+        float a[8], q[8];
+        load8(z + r * C + c0, a);
+        if (RES) load8(res + r * C + c0, q);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float o = fmaxf(fmaf(s[i], a[i], t[i]), 0.f);
-            a[i] = RES ? o + r[i] : o;
+            a[i] = RES ? o + q[i] : o;
         }
-        store8(y + v * 8, a);
+        store8(y + r * C + c0, a);
     }
 }
 
@@ -186,25 +197,42 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dA, 
                                                       const float* __restrict__ scale,
                                                       const float* __restrict__ shift,
                                                       const float* __restrict__ coef, T* __restrict__ dZ,
-                                                      long long nvec, int cv) {
-    const int C = cv * 8;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
-         v += (long long)gridDim.x * blockDim.x) {
-        int c0 = (int)(v % cv) * 8;
-        float a[8], zz[8], s[8], t[8], ca[8], cb[8], cc[8];
-        load8(dA + v * 8, a);
-        load8(z + v * 8, zz);
-        load8(scale + c0, s);
-        load8(shift + c0, t);
-        load8(coef + c0, ca);
-        load8(coef + C + c0, cb);
-        load8(coef + 2 * C + c0, cc);
+                                                      long long M, int C) {
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    float s[8], t[8], ca[8], cb[8], cc[8];
+    load8(scale + c0, s);
+    load8(shift + c0, t);
+    load8(coef + c0, ca);
+    load8(coef + C + c0, cb);
+    load8(coef + 2 * C + c0, cc);
+    const long long stride = (long long)gridDim.y * blockDim.y;
+    long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    for (; r + stride < M; r += 2 * stride) {
+        float a0[8], z0[8], a1[8], z1[8];
+        load8(dA + r * C + c0, a0);
+        load8(z + r * C + c0, z0);
+        load8(dA + (r + stride) * C + c0, a1);
+        load8(z + (r + stride) * C + c0, z1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float g = fmaf(s[i], zz[i], t[i]) > 0.f ? a[i] : 0.f;
-            a[i] = fmaf(ca[i], g, fmaf(cb[i], zz[i], cc[i]));
+            const float g0 = fmaf(s[i], z0[i], t[i]) > 0.f ? a0[i] : 0.f;
+            const float g1 = fmaf(s[i], z1[i], t[i]) > 0.f ? a1[i] : 0.f;
+            a0[i] = fmaf(ca[i], g0, fmaf(cb[i], z0[i], cc[i]));
+            a1[i] = fmaf(ca[i], g1, fmaf(cb[i], z1[i], cc[i]));
         }
-        store8(dZ + v * 8, a);
+        store8(dZ + r * C + c0, a0);
+        store8(dZ + (r + stride) * C + c0, a1);
+    }
+    for (; r < M; r += stride) {
+        float a0[8], z0[8];
+        load8(dA + r * C + c0, a0);
+        load8(z + r * C + c0, z0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float g0 = fmaf(s[i], z0[i], t[i]) > 0.f ? a0[i] : 0.f;
+            a0[i] = fmaf(ca[i], g0, fmaf(cb[i], z0[i], cc[i]));
+        }
+        store8(dZ + r * C + c0, a0);
     }
 }
 
@@ -507,15 +535,14 @@ int mnb_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, c
 int mnb_bn_relu_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y,
                       long long M, int C, int dtype, void* stream) {
     MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_relu_apply: C %% 8 != 0 or M <= 0");
-    long long nvec = M * (C / 8);
-    unsigned g = flat_grid(nvec);
+    ColGeom g = col_geom(M, C, 16);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MNB_F32) {
-        if (residual) bn_relu_apply_k<float, true><<<g, 256, 0, st>>>((const float*)z, scale, shift, (const float*)residual, (float*)y, nvec, C / 8);
-        else bn_relu_apply_k<float, false><<<g, 256, 0, st>>>((const float*)z, scale, shift, nullptr, (float*)y, nvec, C / 8);
+        if (residual) bn_relu_apply_k<float, true><<<g.grid, g.block, 0, st>>>((const float*)z, scale, shift, (const float*)residual, (float*)y, M, C);
+        else bn_relu_apply_k<float, false><<<g.grid, g.block, 0, st>>>((const float*)z, scale, shift, nullptr, (float*)y, M, C);
     } else if (dtype == MNB_BF16) {
-        if (residual) bn_relu_apply_k<bf16, true><<<g, 256, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)residual, (bf16*)y, nvec, C / 8);
-        else bn_relu_apply_k<bf16, false><<<g, 256, 0, st>>>((const bf16*)z, scale, shift, nullptr, (bf16*)y, nvec, C / 8);
+        if (residual) bn_relu_apply_k<bf16, true><<<g.grid, g.block, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)residual, (bf16*)y, M, C);
+        else bn_relu_apply_k<bf16, false><<<g.grid, g.block, 0, st>>>((const bf16*)z, scale, shift, nullptr, (bf16*)y, M, C);
     } else MNB_REQUIRE(false, "bn_relu_apply: bad dtype");
     MNB_LAUNCH_CHECK("bn_relu_apply");
     return 0;
@@ -524,7 +551,8 @@ int mnb_bn_relu_apply(const void* z, const float* scale, const float* shift, con
 int mnb_bn_bwd_reduce(const void* dA, const void* z, const float* scale, const float* shift, double* sums,
                       long long M, int C, int dtype, void* stream) {
     MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_bwd_reduce: C %% 8 != 0 or M <= 0");
-    ColGeom g = col_geom(M, C);
+    // few, fat CTAs: every CTA ends with one fp64 atomic per channel and same-address atomics serialise in L2
+    ColGeom g = col_geom(M, C, 2);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MNB_F32) bn_bwd_reduce_k<float><<<g.grid, g.block, 0, st>>>((const float*)dA, (const float*)z, scale, shift, sums, M, C);
     else if (dtype == MNB_BF16) bn_bwd_reduce_k<bf16><<<g.grid, g.block, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, sums, M, C);
@@ -545,11 +573,10 @@ int mnb_bn_bwd_finalize(const double* sums, const float* scale, const float* sav
 int mnb_bn_bwd_apply(const void* dA, const void* z, const float* scale, const float* shift, const float* coef,
                      void* dZ, long long M, int C, int dtype, void* stream) {
     MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_bwd_apply: C %% 8 != 0 or M <= 0");
-    long long nvec = M * (C / 8);
-    unsigned g = flat_grid(nvec);
+    ColGeom g = col_geom(M, C, 16);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MNB_F32) bn_bwd_apply_k<float><<<g, 256, 0, st>>>((const float*)dA, (const float*)z, scale, shift, coef, (float*)dZ, nvec, C / 8);
-    else if (dtype == MNB_BF16) bn_bwd_apply_k<bf16><<<g, 256, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, coef, (bf16*)dZ, nvec, C / 8);
+    if (dtype == MNB_F32) bn_bwd_apply_k<float><<<g.grid, g.block, 0, st>>>((const float*)dA, (const float*)z, scale, shift, coef, (float*)dZ, M, C);
+    else if (dtype == MNB_BF16) bn_bwd_apply_k<bf16><<<g.grid, g.block, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, coef, (bf16*)dZ, M, C);
     else MNB_REQUIRE(false, "bn_bwd_apply: bad dtype");
     MNB_LAUNCH_CHECK("bn_bwd_apply");
     return 0;

@@ -167,7 +167,9 @@ __device__ __forceinline__ uint4 load_w8(const ConvP& p, int kk2, int nn, int Nt
 // Producer-side position in the (unit, chunk) sequence of this CTA.  Two of these walk the same sequence:
 // `issue` (cp.async) runs D chunks ahead of `finish` (in-place prologue + arrive).
 struct ChunkIt {
-    long long unit, c, cend, m0;
+    int unit, c, cend;
+    int mt;              // fwd/dgrad: M tile, advanced incrementally (no per-tile division)
+    long long m0;
     int n0, stage;
     uint32_t ph;
     int rn, rh, rw;      // decoded row (fwd/dgrad 3x3)
@@ -189,7 +191,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     unsigned char* sC = sBres + bres_bytes;                                   // epilogue stage
     const int c_pitch = BN * 2 + 16;
     const int c_bytes = (MODE == MODE_WGRAD) ? 0 : 128 * c_pitch;
-    float* s_scale = reinterpret_cast<float*>(sC + 2 * c_bytes);
+    // dgrad with fused BN-backward reduction: per-group staging of the producer block's z tile (same geometry as sC)
+    const int z_bytes = (MODE == MODE_DGRAD && p.bn_z != nullptr) ? c_bytes : 0;
+    unsigned char* sZ = sC + 2 * c_bytes;
+    float* s_scale = reinterpret_cast<float*>(sZ + 2 * z_bytes);
     const int xch = (MODE == MODE_DGRAD) ? 0 : p.Cin;
     float* s_shift = s_scale + xch;
     float* s_bias = s_shift + xch;                                            // [128]
@@ -207,8 +212,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     if (MODE == MODE_FWD) { Mtot = (long long)p.N * p.Ho * p.Wo; Ntot = p.Cout; Ktot = (long long)kk2 * p.Cin; }
     else if (MODE == MODE_DGRAD) { Mtot = (long long)p.N * p.H * p.W; Ntot = p.Cin; Ktot = (long long)kk2 * p.Cout; }
     else { Mtot = p.Cout; Ntot = kk2 * p.Cin; Ktot = (long long)p.N * p.Ho * p.Wo; }
-    const long long total_chunks = (Ktot + kc - 1) / kc;
-    const long long units = g.m_tiles * g.n_tiles * g.ksplit;
+    const int total_chunks = (int)((Ktot + kc - 1) / kc);
+    const int units = (int)(g.m_tiles * g.n_tiles * g.ksplit);
+    // fwd/dgrad: gridDim.x is a multiple of n_tiles, so a CTA keeps its N tile and steps its M tile by mt_step
+    const int mt_step = (int)gridDim.x / g.n_tiles;
+    const int mt_first = (int)blockIdx.x / g.n_tiles;
 
     // ---- one-time setup ----
     const bool xf = (MODE != MODE_DGRAD) && p.in_scale != nullptr;
@@ -247,13 +255,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
         const int wpp = tid & 63, wq = tid >> 6;
         auto setup_unit = [&](ChunkIt& it) {
             if (it.unit >= units) return;
-            const int ks = (int)(it.unit % g.ksplit);
-            const int nt = (int)((it.unit / g.ksplit) % g.n_tiles);
-            const long long mt = it.unit / ((long long)g.ksplit * g.n_tiles);
-            it.m0 = mt * 128;
-            it.n0 = nt * BN;
-            long long cbeg = 0, cend = total_chunks;
-            if (MODE == MODE_WGRAD) { cbeg = ks * g.cps; cend = cbeg + g.cps < total_chunks ? cbeg + g.cps : total_chunks; }
+            int cbeg = 0, cend = total_chunks;
+            if (MODE == MODE_WGRAD) {
+                const int ks = it.unit % g.ksplit, t = it.unit / g.ksplit;
+                const int nt = t % g.n_tiles, mt = t / g.n_tiles;
+                it.m0 = (long long)mt * 128;
+                it.n0 = nt * BN;
+                cbeg = ks * (int)g.cps;
+                cend = cbeg + (int)g.cps < total_chunks ? cbeg + (int)g.cps : total_chunks;
+            } else {
+                it.m0 = (long long)it.mt * 128;
+                it.n0 = nt_fixed * BN;
+            }
             it.c = cbeg;
             it.cend = cend;
             if (MODE != MODE_WGRAD) {
@@ -268,13 +281,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
         };
         auto advance = [&](ChunkIt& it) {
             if (++it.stage == NST) { it.stage = 0; it.ph ^= 1; }
-            if (++it.c == it.cend) { it.unit += gridDim.x; setup_unit(it); }
+            if (++it.c == it.cend) { it.unit += gridDim.x; it.mt += mt_step; setup_unit(it); }
         };
         // ---- issue: cp.async the raw vectors of one chunk into its stage (zero-fill where predicated off) ----
         auto issue = [&](ChunkIt& it) {
             mbar_wait(&empty[it.stage], it.ph ^ 1);
             unsigned char* sA = sStage + it.stage * g.stage_bytes;
-            const long long k0 = it.c * kc;
+            const long long k0 = (long long)it.c * kc;
             const int kvalid = (int)((Ktot - k0) < kc ? (Ktot - k0) : kc);
             unsigned mask = 0;
             if (MODE != MODE_WGRAD) {
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
             if (xf) {
                 unsigned char* sA = sStage + it.stage * g.stage_bytes;
                 const unsigned mask = s_mask[it.stage * 256 + tid];
-                const long long k0 = it.c * kc;
+                const long long k0 = (long long)it.c * kc;
                 uint4 q[4];
                 int cch[4];
                 uint4* ptr[4];
@@ -397,6 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
         };
         ChunkIt is, fs;
         is.unit = fs.unit = blockIdx.x;
+        is.mt = fs.mt = mt_first;
         is.stage = fs.stage = 0;
         is.ph = fs.ph = 0;
         is.c = is.cend = fs.c = fs.cend = 0;
@@ -421,19 +435,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
             const uint32_t idesc = make_idesc(BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
             int stage = 0, a = 0;
             uint32_t ph = 0, aph = 0;
-            for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
-                const int ks = (int)(unit % g.ksplit);
-                long long cbeg = 0, cend = total_chunks;
-                if (MODE == MODE_WGRAD) { cbeg = ks * g.cps; cend = cbeg + g.cps < total_chunks ? cbeg + g.cps : total_chunks; }
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                int cbeg = 0, cend = total_chunks;
+                if (MODE == MODE_WGRAD) {
+                    const int ks = unit % g.ksplit;
+                    cbeg = ks * (int)g.cps;
+                    cend = cbeg + (int)g.cps < total_chunks ? cbeg + (int)g.cps : total_chunks;
+                }
                 mbar_wait(&acc_empty[a], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
                 bool first = true;
-                for (long long c = cbeg; c < cend; ++c) {
+                for (int c = cbeg; c < cend; ++c) {
                     mbar_wait(&full[stage], ph);
                     tc_fence_after();
                     const uint32_t sA_u = smem_u32(sStage + stage * g.stage_bytes);
-                    const long long k0 = c * kc;
+                    const long long k0 = (long long)c * kc;
                     const int kvalid = (int)((Ktot - k0) < kc ? (Ktot - k0) : kc);
                     const int k16 = (kvalid + 15) >> 4;
                     for (int j = 0; j < k16; ++j) {
@@ -477,14 +494,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
         float sacc[8], qacc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) sacc[j] = qacc[j] = 0.f;
-        const bool do_stats = (MODE == MODE_FWD) && p.stats != nullptr;
-        long long local = 0;
-        for (long long unit = blockIdx.x; unit < units; unit += gridDim.x, ++local) {
+        const bool do_stats = (MODE == MODE_FWD && p.stats != nullptr) ||
+                              (MODE == MODE_DGRAD && p.stats != nullptr && p.bn_z != nullptr);
+        const int Cs = (MODE == MODE_FWD) ? p.Cout : p.Cin;      // channel count of the statistics vector
+        float bs[8], bt[8];                                        // dgrad: producer block's BN scale/shift
+        if (MODE == MODE_DGRAD && do_stats) {
+            const int col = nt_fixed * BN + c8o * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bs[j] = col + j < Ntot ? p.bn_scale[col + j] : 0.f;
+                bt[j] = col + j < Ntot ? p.bn_shift[col + j] : 0.f;
+            }
+        }
+        int local = 0, mt_e = mt_first;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++local, mt_e += mt_step) {
             if ((local & 1) != grp) continue;
-            const int nt = (int)((unit / g.ksplit) % g.n_tiles);
-            const long long mt = unit / ((long long)g.ksplit * g.n_tiles);
-            const long long m0 = mt * 128;
+            int nt = nt_fixed, mt = mt_e;
+            if (MODE == MODE_WGRAD) { const int t = unit / g.ksplit; nt = t % g.n_tiles; mt = t / g.n_tiles; }
+            const long long m0 = (long long)mt * 128;
             const int n0 = nt * BN;
+            if (MODE == MODE_DGRAD && do_stats && pass_active) {
+                // prefetch this thread's vectors of the producer block's z tile; lands while we wait for the MMAs
+                const int rows_here = (int)(Mtot - m0 < 128 ? Mtot - m0 : 128);
+                const int col = n0 + c8o * 8;
+                if (col < Ntot)
+                    for (int row = rgo; row < rows_here; row += groups)
+                        cp_async16(sZ + grp * z_bytes + row * c_pitch + c8o * 16,
+                                   (const bf16*)p.bn_z + (m0 + row) * (long long)p.Cin + col, true);
+                cp_async_commit();
+            }
             mbar_wait(&acc_full[grp], aph);
             aph ^= 1;
             tc_fence_after();
@@ -551,6 +589,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                 tc_fence_before();
                 mbar_arrive(&acc_empty[grp]);          // accumulator drained: the MMA warp may reuse it
                 named_bar_sync(1 + grp, 128);
+                if (MODE == MODE_DGRAD && do_stats) cp_async_wait<0>();
                 if (pass_active) {
                     const int rows_here = (int)(Mtot - m0 < 128 ? Mtot - m0 : 128);
                     const int col = n0 + c8o * 8;
@@ -564,8 +603,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                             if (do_stats) {
                                 float x[8];
                                 unpack_bf16x8(q, x);
+                                if (MODE == MODE_FWD) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) { sacc[j] += x[j]; qacc[j] = fmaf(x[j], x[j], qacc[j]); }
+                                    for (int j = 0; j < 8; ++j) { sacc[j] += x[j]; qacc[j] = fmaf(x[j], x[j], qacc[j]); }
+                                } else {
+                                    // fused BN-backward reduction: G = dx*[s*z+t>0]; sum G, sum G*z
+                                    float zz[8];
+                                    unpack_bf16x8(*reinterpret_cast<const uint4*>(sZ + grp * z_bytes + row * c_pitch + c8o * 16), zz);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float gg = fmaf(bs[j], zz[j], bt[j]) > 0.f ? x[j] : 0.f;
+                                        sacc[j] += gg;
+                                        qacc[j] = fmaf(gg, zz[j], qacc[j]);
+                                    }
+                                }
                             }
                         }
                     }
@@ -589,7 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
             for (int i = et; i < BN; i += 128)
                 if (n0 + i < Ntot) {
                     atomicAdd(&p.stats[n0 + i], (double)s_redg[i]);
-                    atomicAdd(&p.stats[p.Cout + n0 + i], (double)s_redg[BN + i]);
+                    atomicAdd(&p.stats[Cs + n0 + i], (double)s_redg[BN + i]);
                 }
         }
     }
@@ -626,7 +677,8 @@ static bool tc_geom(int mode, const ConvP& p, TcGeom& g, size_t& smem, int& dept
     g.stage_bytes = 128 * g.kc * 2 + ((mode == MODE_WGRAD || !g.b_resident) ? BN * g.kc * 2 : 0);
     const int xch = mode == MODE_DGRAD ? 0 : p.Cin;
     const size_t fixed = (g.b_resident ? (size_t)BN * g.kpad * 2 : 0) +
-                         (mode == MODE_WGRAD ? 0 : (size_t)2 * 128 * (BN * 2 + 16)) + (size_t)2 * xch * 4 + (128 + 512) * 4 +
+                         (mode == MODE_WGRAD ? 0 : (size_t)2 * 128 * (BN * 2 + 16)) +
+                         ((mode == MODE_DGRAD && p.bn_z) ? (size_t)2 * 128 * (BN * 2 + 16) : 0) + (size_t)2 * xch * 4 + (128 + 512) * 4 +
                          (2 * MAXSTAGE + 4) * 8 + 16 + MAXSTAGE * 256 + 128;
     // deep ring of small stages when the chunk is small (memory-level parallelism), else 5 x up to 32 KB
     depth = ((size_t)10 * g.stage_bytes + fixed <= 220 * 1024) ? 8 : 3;

@@ -150,7 +150,8 @@ class ParamStore:
 class _ConvApp:
     """One application of a ConvBlock inside a plan."""
     __slots__ = ("cb", "inp", "z", "stats", "sums", "scale", "shift", "mean", "invstd", "coef", "kind",
-                 "Ho", "Wo", "Cout", "k", "stride", "pad", "need_dgrad", "m", "in_bytes", "out_bytes", "label")
+                 "Ho", "Wo", "Cout", "k", "stride", "pad", "need_dgrad", "m", "in_bytes", "out_bytes", "label",
+                 "index", "reduce_fused")
 
 
 class Plan:
@@ -303,6 +304,7 @@ class Plan:
             else:
                 self._op(ops, "mnb_bn_eval_coeffs", bn.weight, bn.bias, bn.running_mean, bn.running_var,
                          a.scale, a.shift, cout, float(bn.eps))
+        a.index, a.reduce_fused = len(self.apps), False
         self.apps.append(a)
         self.tape.append(("conv", a))
         return Ref(a.z, ref.N, Ho, Wo, cout, a.scale, a.shift)
@@ -403,8 +405,9 @@ class Plan:
                 M, C = int(a.m), a.Cout
                 self._cur_detail = f"{a.inp.H}x{a.inp.W} {a.inp.C}->{a.Cout} k{a.k}s{a.stride}"
                 dz = free.pop()
-                self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
-                         nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
+                if not a.reduce_fused:     # else: done in the epilogue of the dgrad that produced gbuf
+                    self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
+                             nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
                 self._op(ops, "mnb_bn_bwd_finalize", a.sums, a.scale, a.mean, a.invstd, _G(bn.weight),
                          _G(bn.bias), _G(conv.bias), a.coef, C, a.m)
                 self._op(ops, "mnb_bn_bwd_apply", gbuf, a.z, a.scale, a.shift, a.coef, dz, M, C, self.code,
@@ -428,14 +431,21 @@ class Plan:
                     add = None
                     if idx > 0 and self.tape[idx - 1][0] == "res_begin":
                         add = held[-1]
+                    # dx is the dA of the ConvBlock applied just before this one: fuse its BN-backward
+                    # reduction (sum G, sum G*z) into this dgrad's epilogue
+                    pa = self.apps[a.index - 1] if (a.index > 0 and eng.fuse_bn_reduce) else None
+                    bn = (pa.z, pa.scale, pa.shift, pa.sums) if pa is not None else (None, None, None, None)
+                    if pa is not None:
+                        pa.reduce_fused = True
+                    extra = a.in_bytes if pa is not None else 0
                     if a.kind == "dense":
-                        self._op(ops, "mnb_conv_dgrad", dz, conv.weight, add, dx, r.N, r.H, r.W, r.C, C, a.k,
+                        self._op(ops, "mnb_conv_dgrad", dz, conv.weight, add, dx, *bn, r.N, r.H, r.W, r.C, C, a.k,
                                  a.stride, a.pad, self.code, eng.impl,
-                                 nbytes=a.in_bytes * (2 if add is not None else 1) + a.out_bytes,
+                                 nbytes=a.in_bytes * (2 if add is not None else 1) + a.out_bytes + extra,
                                  label=a.label + "_dgrad")
                     else:
-                        self._op(ops, "mnb_dw_dgrad", dz, conv.weight, dx, r.N, r.H, r.W, r.C, a.k, self.code,
-                                 nbytes=a.in_bytes + a.out_bytes, label=a.label + "_dgrad")
+                        self._op(ops, "mnb_dw_dgrad", dz, conv.weight, dx, *bn, r.N, r.H, r.W, r.C, a.k, self.code,
+                                 nbytes=a.in_bytes + a.out_bytes + extra, label=a.label + "_dgrad")
                     free.append(dz)
                     gbuf = dx
                 else:
@@ -611,6 +621,8 @@ class Engine:
         self.grad_hook = None          # DDP: callable(engine, stage) invoked while backward is enqueued
         self.graphs = {}
         self.world_size = 1
+        self.fuse_bn_reduce = False    # BN-backward reductions in the producing dgrad epilogue (tested; off:
+                                       # the dgrad epilogues are the bottleneck, the separate kernel is faster)
         self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
 
     def plan(self, N, H, W) -> Plan:

@@ -29,7 +29,7 @@ for i in range(reps + 1):
     if mode == "fwd":
         L.call("mnb_conv_fwd", P(x), P(s), P(t), P(w), P(b), P(z), P(stats), N, H, W, Cin, Cout, k, stride, pad, 1, 0, 0, st)
     elif mode == "dgrad":
-        L.call("mnb_conv_dgrad", P(dz), P(w), None, P(dx), N, H, W, Cin, Cout, k, stride, pad, 1, 0, st)
+        L.call("mnb_conv_dgrad", P(dz), P(w), None, P(dx), None, None, None, None, N, H, W, Cin, Cout, k, stride, pad, 1, 0, st)
     elif mode == "wgrad":
         L.call("mnb_conv_wgrad", P(x), P(s), P(t), P(dz), P(dw), N, H, W, Cin, Cout, k, stride, pad, 1, 0, 0, st)
     elif mode.startswith("dw"):
@@ -37,7 +37,7 @@ for i in range(reps + 1):
         if mode.endswith("fwd"):
             L.call("mnb_dw_fwd", P(x), P(s), P(t), P(w), P(b), P(z), P(stats), N, H, W, Cin, kk, 1, st)
         elif mode.endswith("dgrad"):
-            L.call("mnb_dw_dgrad", P(dz), P(w), P(dx), N, H, W, Cin, kk, 1, st)
+            L.call("mnb_dw_dgrad", P(dz), P(w), P(dx), None, None, None, None, N, H, W, Cin, kk, 1, st)
         else:
             L.call("mnb_dw_wgrad", P(x), P(s), P(t), P(dz), P(dw), N, H, W, Cin, kk, 1, st)
 ev[1].record()

@@ -111,8 +111,18 @@ def test_conv_fwd_dgrad_wgrad(case, dtype, impl):
     add = torch.randn(N, Cin, H, W, generator=g, dtype=torch.float64)
     addd = nhwc(add, dtype)
     dx = torch.empty(N, H, W, Cin, device="cuda", dtype=tdt(dtype))
-    L.call("mnb_conv_dgrad", P(dzd), P(wd), P(addd), P(dx), N, H, W, Cin, Cout, k, stride, pad, code(dtype), im,
-           stream())
+    # fused BN-backward reduction of the producer block in the dgrad epilogue == mnb_bn_bwd_reduce on dx
+    gq = torch.Generator().manual_seed(11)
+    bz = nhwc(torch.randn(N, Cin, H, W, generator=gq, dtype=torch.float64), dtype)
+    bsc = (torch.rand(Cin, generator=gq) + 0.5).cuda()
+    bsh = (torch.randn(Cin, generator=gq) * 0.3).cuda()
+    fused = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
+    L.call("mnb_conv_dgrad", P(dzd), P(wd), P(addd), P(dx), P(bz), P(bsc), P(bsh), P(fused), N, H, W, Cin, Cout, k,
+           stride, pad, code(dtype), im, stream())
+    sep = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
+    L.call("mnb_bn_bwd_reduce", P(dx), P(bz), P(bsc), P(bsh), P(sep), N * H * W, Cin, code(dtype), stream())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(fused, sep, rtol=1e-4, atol=1e-4 * sep.abs().max().item())
     dw = torch.zeros(Cout, Cin, k, k, device="cuda", dtype=torch.float32)
     L.call("mnb_conv_wgrad", P(xd), P(sd), P(td), P(dzd), P(dw), N, H, W, Cin, Cout, k, stride, pad, code(dtype), 0,
            im, stream())
@@ -191,7 +201,20 @@ def test_depthwise_fwd_dgrad_wgrad(case, dtype):
     w_ = w.double().requires_grad_(True)
     F.conv2d(a_, w_, None, padding=k // 2, groups=C).backward(dz)
     dx = torch.empty(N, H, W, C, device="cuda", dtype=tdt(dtype))
-    L.call("mnb_dw_dgrad", P(dzd), P(wd), P(dx), N, H, W, C, k, code(dtype), stream())
+    gq = torch.Generator().manual_seed(12)
+    bz = nhwc(torch.randn(N, C, H, W, generator=gq, dtype=torch.float64), dtype)
+    bsc = (torch.rand(C, generator=gq) + 0.5).cuda()
+    bsh = (torch.randn(C, generator=gq) * 0.3).cuda()
+    fused = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    L.call("mnb_dw_dgrad", P(dzd), P(wd), P(dx), P(bz), P(bsc), P(bsh), P(fused), N, H, W, C, k, code(dtype), stream())
+    sep = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    L.call("mnb_bn_bwd_reduce", P(dx), P(bz), P(bsc), P(bsh), P(sep), N * H * W, C, code(dtype), stream())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(fused, sep, rtol=1e-4, atol=1e-4 * sep.abs().max().item())
+    dx2 = torch.empty_like(dx)
+    L.call("mnb_dw_dgrad", P(dzd), P(wd), P(dx2), None, None, None, None, N, H, W, C, k, code(dtype), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx2)
     dw = torch.zeros(C, 1, k, k, device="cuda")
     L.call("mnb_dw_wgrad", P(xd), P(sd), P(td), P(dzd), P(dw), N, H, W, C, k, code(dtype), stream())
     torch.cuda.synchronize()
