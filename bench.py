@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table (JSON) here")
+    ap.add_argument("--dump-ops", default=None, help="write the launch sequence of one step (labels) here")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -196,6 +197,19 @@ def main():
     nbuf = 2                                           # alternate two resident batches (each 154 MB > L2)
     xs = [torch.randn(N, 3, S, S, device=dev, generator=g) for _ in range(nbuf)]
     ts = [torch.randint(0, 1000, (N,), device=dev, generator=g) for _ in range(nbuf)]
+    if args.dump_ops and rank == 0:
+        plan = eng.plan(N, S, S)
+        seq = []
+        for op in plan.fwd:
+            seq.append([getattr(op, "label", op.name), getattr(op, "detail", ""), op.name])
+        seq.append(["xent", "", "mnb_xent_fwd_bwd"])
+        for op in plan.bwd:
+            seq.append([getattr(op, "label", op.name), getattr(op, "detail", ""), op.name])
+            if op.name == "mnb_fc_wgrad":
+                seq.append(["fc_wgrad_bias", "", "mnb_fc_wgrad"])
+        seq += [["counter_inc", "", "mnb_counter_inc"], ["adam", "", "mnb_adam_step"]]
+        with open(args.dump_ops, "w") as f:
+            json.dump(seq, f)
     use_graph = world == 1 and not args.no_graph
     step_fn = eng.train_step_graph if use_graph else eng.train_step
 
@@ -312,8 +326,16 @@ def main():
                          "frac_of_hbm_peak": ((v[2] / 1e9) / (v[1] / 1e3)) / hbm if v[1] > 0 else 0.0}
                         for k, v in agg.items()), key=lambda r: -r["ms_per_step"])
         top = next(r for r in table if r["algorithmic_GB_per_step"] > 0)
+        traffic = None
+        try:    # dram__bytes_read+write per step for this kernel class, from the committed ncu pass (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r1_ncu_step_summary.json")) as f:
+                traffic = json.load(f)["classes"][top["kernel"]]["dram_GB_per_step"]
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_GBps"], "peak": hbm,
-                "unit": "GB/s", "frac": top["achieved_GBps"] / hbm, "traffic": None, "peak_source": which,
+                "unit": "GB/s", "frac": top["achieved_GBps"] / hbm, "traffic": traffic,
+                "traffic_unit": "GB per step over this kernel class's launches (ncu dram__bytes_read+write)",
+                "peak_source": which,
                 "share_of_step": top["share"],
                 "step_algorithmic_GB": sum(r["algorithmic_GB_per_step"] for r in table),
                 "step_frac_of_hbm_peak": (value / world) * 117.17e6 / 1e9 / hbm}
