@@ -50,6 +50,19 @@ int mnb_device_is_sm100(void);
 int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                  void* z, double* stats, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                  int dtype, int x_layout, int impl, void* stream);
+/* Optional bf16 re-layout of a dense conv weight for the tcgen05 path (call once per optimizer step):
+ *   wpk_fwd  [Cout][k*k*Cin]  with kk = (kh*k+kw)*Cin + ci   (K-major B operand of the forward GEMM)
+ *   wpk_dgrad[Cin ][k*k*Cout] with kk = (kh*k+kw)*Cout + co  (K-major B operand of the backward-data GEMM)
+ * Either pointer may be NULL.  Register the result with mnb_conv_fwd_packed / mnb_conv_dgrad_packed. */
+int mnb_pack_weights(const float* w, void* wpk_fwd, void* wpk_dgrad, int Cout, int Cin, int k, void* stream);
+/* Same as mnb_conv_fwd / mnb_conv_dgrad (bf16, tcgen05) with the pre-packed weight: the GEMM producers then copy
+ * the B operand with 16-byte cp.async instead of gathering fp32 scalars. */
+int mnb_conv_fwd_packed(const void* x, const float* in_scale, const float* in_shift, const float* w,
+                        const void* wpk_fwd, const float* bias, void* z, double* stats, int N, int H, int W, int Cin,
+                        int Cout, int k, int stride, int pad, int dtype, int x_layout, int impl, void* stream);
+int mnb_conv_dgrad_packed(const void* dz, const float* w, const void* wpk_dgrad, const void* add, void* dx,
+                          const void* bn_z, const float* bn_scale, const float* bn_shift, double* bn_sums, int N, int H,
+                          int W, int Cin, int Cout, int k, int stride, int pad, int dtype, int impl, void* stream);
 /* dx[n,h,w,ci] = (add ? add[n,h,w,ci] : 0) + sum dz[n,ho,wo,co]*w[co,ci,kh,kw]   (conv backward-data)
  * Optional fused BatchNorm-backward reduction for the ConvBlock that PRODUCED this conv's input (dx is its dA):
  * when bn_z != NULL, bn_sums[0:Cin] += sum G and bn_sums[Cin:2Cin] += sum G*z with

@@ -11,6 +11,7 @@ struct ConvP {
     const float* in_scale;
     const float* in_shift;
     const float* w;       // [Cout,Cin,k,k]
+    const void* wpk;      // optional bf16 K-major packing of w for this GEMM (mnb_pack_weights)
     const float* bias;
     const void* dz;       // dgrad/wgrad
     const void* add;      // dgrad residual

@@ -283,6 +283,17 @@ int stem_fwd(const float* x, const float* w, const float* bias, void* z, double*
              cudaStream_t st);
 int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, int dtype, cudaStream_t st);
 
+__global__ void pack_weights_k(const float* __restrict__ w, bf16* __restrict__ pf, bf16* __restrict__ pd, int Cout,
+                               int Cin, int kk2) {
+    const int total = Cout * Cin * kk2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % kk2, ci = (i / kk2) % Cin, co = i / (kk2 * Cin);      // torch layout [co][ci][tap]
+        const bf16 v = __float2bfloat16_rn(w[i]);
+        if (pf) pf[(long long)co * kk2 * Cin + tap * Cin + ci] = v;
+        if (pd) pd[(long long)ci * kk2 * Cout + tap * Cout + co] = v;
+    }
+}
+
 static int check_conv(const char* name, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dtype,
                       int x_layout) {
     MNB_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0, "%s: bad N/H/W/Cin", name);
@@ -332,11 +343,36 @@ using namespace mnb;
 
 extern "C" {
 
+int mnb_pack_weights(const float* w, void* wpk_fwd, void* wpk_dgrad, int Cout, int Cin, int k, void* stream) {
+    MNB_REQUIRE(Cout > 0 && Cin > 0 && (k == 1 || k == 3), "pack_weights: bad shape");
+    const int total = Cout * Cin * k * k;
+    int blocks = (total + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    pack_weights_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wpk_fwd, (bf16*)wpk_dgrad, Cout, Cin, k * k);
+    MNB_LAUNCH_CHECK("pack_weights");
+    return 0;
+}
+
 int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                  void* z, double* stats, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dtype,
                  int x_layout, int impl, void* stream) {
+    return mnb_conv_fwd_packed(x, in_scale, in_shift, w, nullptr, bias, z, stats, N, H, W, Cin, Cout, k, stride, pad,
+                               dtype, x_layout, impl, stream);
+}
+
+int mnb_conv_dgrad(const void* dz, const float* w, const void* add, void* dx, const void* bn_z, const float* bn_scale,
+                   const float* bn_shift, double* bn_sums, int N, int H, int W, int Cin, int Cout, int k, int stride,
+                   int pad, int dtype, int impl, void* stream) {
+    return mnb_conv_dgrad_packed(dz, w, nullptr, add, dx, bn_z, bn_scale, bn_shift, bn_sums, N, H, W, Cin, Cout, k,
+                                 stride, pad, dtype, impl, stream);
+}
+
+int mnb_conv_fwd_packed(const void* x, const float* in_scale, const float* in_shift, const float* w, const void* wpk,
+                        const float* bias, void* z, double* stats, int N, int H, int W, int Cin, int Cout, int k,
+                        int stride, int pad, int dtype, int x_layout, int impl, void* stream) {
     if (int e = check_conv("conv_fwd", N, H, W, Cin, Cout, k, stride, pad, dtype, x_layout)) return e;
     ConvP p = {};
+    p.wpk = wpk;
     p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.w = w; p.bias = bias; p.out = z; p.stats = stats;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
@@ -351,12 +387,13 @@ int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, co
     return conv_fwd_simt(p, dtype, (cudaStream_t)stream);
 }
 
-int mnb_conv_dgrad(const void* dz, const float* w, const void* add, void* dx, const void* bn_z, const float* bn_scale,
-                   const float* bn_shift, double* bn_sums, int N, int H, int W, int Cin, int Cout, int k, int stride,
-                   int pad, int dtype, int impl, void* stream) {
+int mnb_conv_dgrad_packed(const void* dz, const float* w, const void* wpk, const void* add, void* dx, const void* bn_z,
+                          const float* bn_scale, const float* bn_shift, double* bn_sums, int N, int H, int W, int Cin,
+                          int Cout, int k, int stride, int pad, int dtype, int impl, void* stream) {
     if (int e = check_conv("conv_dgrad", N, H, W, Cin, Cout, k, stride, pad, dtype, MNB_LAYOUT_NHWC)) return e;
     MNB_REQUIRE(!bn_z || (bn_scale && bn_shift && bn_sums), "conv_dgrad: bn_z needs bn_scale/bn_shift/bn_sums");
     ConvP p = {};
+    p.wpk = wpk;
     p.dz = dz; p.w = w; p.add = add; p.out = dx;
     p.bn_z = bn_z; p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.stats = bn_z ? bn_sums : nullptr;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;

@@ -141,6 +141,10 @@ __device__ __forceinline__ uint4 xform8(uint4 u, const float* s_scale, const flo
 // weight vector for the K-major B operand: 8 consecutive kk of column nn (fp32 torch layout -> bf16x8)
 template <int MODE>
 __device__ __forceinline__ uint4 load_w8(const ConvP& p, int kk2, int nn, int Ntot, long long kk, long long Ktot) {
+    if (p.wpk) {        // pre-packed bf16 [Ntot][Ktot], K contiguous
+        if (nn < Ntot && kk < Ktot) return *reinterpret_cast<const uint4*>((const bf16*)p.wpk + (long long)nn * Ktot + kk);
+        return make_uint4(0, 0, 0, 0);
+    }
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -331,9 +335,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int k8 = 2 * i + ppar;
-                        if (k8 < nk8)
-                            *reinterpret_cast<uint4*>(sB + ((k8 * BN) + prow) * 16) =
-                                load_w8<MODE>(p, kk2, it.n0 + prow, Ntot, k0 + k8 * 8, Ktot);
+                        if (k8 < nk8) {
+                            if (p.wpk) {        // packed bf16 weights: asynchronous, like the A operand
+                                const int nn = it.n0 + prow;
+                                const long long kk = k0 + k8 * 8;
+                                const bool pred = nn < Ntot && kk < Ktot;
+                                cp_async16(sB + ((k8 * BN) + prow) * 16,
+                                           pred ? (const bf16*)p.wpk + (long long)nn * Ktot + kk : (const bf16*)p.wpk, pred);
+                            } else {
+                                *reinterpret_cast<uint4*>(sB + ((k8 * BN) + prow) * 16) =
+                                    load_w8<MODE>(p, kk2, it.n0 + prow, Ntot, k0 + k8 * 8, Ktot);
+                            }
+                        }
                     }
                 }
             } else {

@@ -47,9 +47,18 @@ DECLS = parse_header()
 
 
 def _load():
-    if not os.path.exists(LIB_PATH) or os.environ.get("MNB200_REBUILD"):
-        from . import build
-        build.build(force=bool(os.environ.get("MNB200_REBUILD")))
+    from . import build
+    stale = False
+    try:
+        stale = build.needs_build()          # sources / header newer than the library
+    except Exception:
+        stale = not os.path.exists(LIB_PATH)
+    if stale or os.environ.get("MNB200_REBUILD"):
+        try:
+            build.build(force=bool(os.environ.get("MNB200_REBUILD")))
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise                        # no library and no way to build it: fail loudly
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argl) in DECLS.items():
         fn = getattr(lib, name)          # AttributeError -> header/library mismatch: fail loudly

@@ -168,6 +168,7 @@ class Plan:
         self.tape = []
         self.generation = 0
         self.last_write = {}
+        self.packed = {}
         self._arena_f, self._arena_d = [], []   # (numel) requests
         self._build()
 
@@ -288,10 +289,11 @@ class Plan:
         a.in_bytes, a.out_bytes = in_b, out_b
         a.label = f"dw{k}x{k}" if a.kind == "dw" else (f"conv{k}x{k}" if k > 1 else "pw1x1")
         self._cur_detail = f"{ref.H}x{ref.W} {cin}->{cout} k{k}s{stride}"
+        wpk = self._packed(cb) if (a.kind == "dense" and not ref.nchw and eng.dtype == "bf16") else (None, None)
         for ops, train in ((self.fwd, True), (self.fwd_eval, False)):
             st = a.stats if train else None
             if a.kind == "dense":
-                self._op(ops, "mnb_conv_fwd", x_t, ref.scale, ref.shift, conv.weight, conv.bias, a.z, st,
+                self._op(ops, "mnb_conv_fwd_packed", x_t, ref.scale, ref.shift, conv.weight, wpk[0], conv.bias, a.z, st,
                          ref.N, ref.H, ref.W, cin, cout, k, stride, pad, self.code, layout, eng.impl,
                          nbytes=in_b + out_b, label=a.label + "_fwd")
             else:
@@ -308,6 +310,22 @@ class Plan:
         self.apps.append(a)
         self.tape.append(("conv", a))
         return Ref(a.z, ref.N, Ho, Wo, cout, a.scale, a.shift)
+
+    def _packed(self, cb):
+        """bf16 K-major packings (forward, backward-data) of a dense ConvBlock's weight, refreshed once per
+        forward (shared-weight blocks are packed once, before their first application)."""
+        key = id(cb)
+        if key not in self.packed:
+            conv = cb.conv
+            n = conv.weight.numel()
+            pf = torch.empty(n, device=self.dev, dtype=torch.bfloat16)
+            pd = torch.empty(n, device=self.dev, dtype=torch.bfloat16)
+            self.keep += [pf, pd]
+            self.packed[key] = (pf, pd)
+            for ops in (self.fwd, self.fwd_eval):
+                self._op(ops, "mnb_pack_weights", conv.weight, pf, pd if ops is self.fwd else None,
+                         conv.out_channels, conv.in_channels, conv.kernel_size[0], label="pack_weights")
+        return self.packed[key]
 
     def _emit_head(self, mod, ref: Ref):
         """AdaptiveAvgPool2d(1) + classifier Sequential of Dropout / Linear / ReLU (classifiers.py:56-111)."""
@@ -439,7 +457,8 @@ class Plan:
                         pa.reduce_fused = True
                     extra = a.in_bytes if pa is not None else 0
                     if a.kind == "dense":
-                        self._op(ops, "mnb_conv_dgrad", dz, conv.weight, add, dx, *bn, r.N, r.H, r.W, r.C, C, a.k,
+                        wpk_d = self.packed[id(a.cb)][1] if id(a.cb) in self.packed else None
+                        self._op(ops, "mnb_conv_dgrad_packed", dz, conv.weight, wpk_d, add, dx, *bn, r.N, r.H, r.W, r.C, C, a.k,
                                  a.stride, a.pad, self.code, eng.impl,
                                  nbytes=a.in_bytes * (2 if add is not None else 1) + a.out_bytes + extra,
                                  label=a.label + "_dgrad")
