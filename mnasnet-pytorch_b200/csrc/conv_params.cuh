@@ -23,6 +23,9 @@ struct ConvP {
     const float* bn_shift;
     int N, H, W, Cin, Ho, Wo, Cout, k, stride, pad;
     int nchw_in;          // x is NCHW fp32
+    // stride-2 3x3 backward-data, decomposed by input-position parity (ph_h, ph_w): only the taps with
+    // (h+1-kh) and (w+1-kw) even contribute -> 4 dense sub-problems with 1/2/2/4 taps instead of 9 mostly-zero ones
+    int phase_mode, ph_h, ph_w;
     long long kchunk;     // wgrad: positions per blockIdx.z
 };
 

@@ -138,9 +138,32 @@ __device__ __forceinline__ uint4 xform8(uint4 u, const float* s_scale, const flo
     return pack_bf16x8(v);
 }
 
+// stride-2 dgrad phase: local tap index -> (global tap kh*3+kw, output-row offset dh, output-col offset dw)
+__device__ __forceinline__ void phase_tap(const ConvP& p, int t_local, int& tap_g, int& dh, int& dw) {
+    const int nkw = p.ph_w ? 2 : 1;
+    const int ikh = t_local / nkw, ikw = t_local - ikh * nkw;
+    const int kh = p.ph_h ? ikh * 2 : 1, kw = p.ph_w ? ikw * 2 : 1;
+    tap_g = kh * 3 + kw;
+    dh = (p.ph_h + 1 - kh) >> 1;
+    dw = (p.ph_w + 1 - kw) >> 1;
+}
+
 // weight vector for the K-major B operand: 8 consecutive kk of column nn (fp32 torch layout -> bf16x8)
 template <int MODE>
 __device__ __forceinline__ uint4 load_w8(const ConvP& p, int kk2, int nn, int Ntot, long long kk, long long Ktot) {
+    if (MODE == MODE_DGRAD && p.phase_mode) {
+        if (!(nn < Ntot && kk < Ktot)) return make_uint4(0, 0, 0, 0);
+        const int t_local = (int)(kk / p.Cout), co = (int)(kk - (long long)t_local * p.Cout);
+        int tap_g, dh, dw;
+        phase_tap(p, t_local, tap_g, dh, dw);
+        if (p.wpk) return *reinterpret_cast<const uint4*>((const bf16*)p.wpk + ((long long)nn * 9 + tap_g) * p.Cout + co);
+        float v[8];
+        const float* wp = p.w + ((long long)co * p.Cin + nn) * 9 + tap_g;
+        const long long cs = (long long)p.Cin * 9;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = wp[i * cs];
+        return pack_bf16x8(v);
+    }
     if (p.wpk) {        // pre-packed bf16 [Ntot][Ktot], K contiguous
         if (nn < Ntot && kk < Ktot) return *reinterpret_cast<const uint4*>((const bf16*)p.wpk + (long long)nn * Ktot + kk);
         return make_uint4(0, 0, 0, 0);
@@ -216,6 +239,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     if (MODE == MODE_FWD) { Mtot = (long long)p.N * p.Ho * p.Wo; Ntot = p.Cout; Ktot = (long long)kk2 * p.Cin; }
     else if (MODE == MODE_DGRAD) { Mtot = (long long)p.N * p.H * p.W; Ntot = p.Cin; Ktot = (long long)kk2 * p.Cout; }
     else { Mtot = p.Cout; Ntot = kk2 * p.Cin; Ktot = (long long)p.N * p.Ho * p.Wo; }
+    const bool phase = (MODE == MODE_DGRAD) && p.phase_mode;
+    const int Hp = phase ? (p.H - p.ph_h + 1) / 2 : p.H, Wp = phase ? (p.W - p.ph_w + 1) / 2 : p.W;
+    if (phase) { Mtot = (long long)p.N * Hp * Wp; Ktot = (long long)(p.ph_h ? 2 : 1) * (p.ph_w ? 2 : 1) * p.Cout; }
     const int total_chunks = (int)((Ktot + kc - 1) / kc);
     const int units = (int)(g.m_tiles * g.n_tiles * g.ksplit);
     // fwd/dgrad: gridDim.x is a multiple of n_tiles, so a CTA keeps its N tile and steps its M tile by mt_step
@@ -278,7 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                 it.row_ok = m < Mtot;
                 it.rn = it.rh = it.rw = 0;
                 if (it.row_ok && !is1x1) {
-                    const int Wd = MODE == MODE_FWD ? p.Wo : p.W, Hd = MODE == MODE_FWD ? p.Ho : p.H;
+                    const int Wd = MODE == MODE_FWD ? p.Wo : Wp, Hd = MODE == MODE_FWD ? p.Ho : Hp;
                     it.rw = (int)(m % Wd); it.rh = (int)((m / Wd) % Hd); it.rn = (int)(m / ((long long)Wd * Hd));
                 }
             }
@@ -317,6 +343,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                                 const int ih = it.rh * p.stride - p.pad + kh, iw = it.rw * p.stride - p.pad + kw;
                                 pred = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
                                 if (pred) src = src0 + (((long long)it.rn * p.H + ih) * p.W + iw) * p.Cin + cc;
+                            } else if (phase) {
+                                int tap_g, dh, dw;
+                                phase_tap(p, tap, tap_g, dh, dw);       // `tap` is the phase-local tap index here
+                                const int ho = it.rh + dh, wo = it.rw + dw;
+                                pred = ho < p.Ho && wo < p.Wo;
+                                if (pred) src = src0 + (((long long)it.rn * p.Ho + ho) * p.Wo + wo) * p.Cout + cc;
                             } else {
                                 const int hn = it.rh + p.pad - kh, wn = it.rw + p.pad - kw;
                                 pred = hn >= 0 && wn >= 0 && hn % p.stride == 0 && wn % p.stride == 0;
@@ -336,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                     for (int i = 0; i < 4; ++i) {
                         const int k8 = 2 * i + ppar;
                         if (k8 < nk8) {
-                            if (p.wpk) {        // packed bf16 weights: asynchronous, like the A operand
+                            if (p.wpk && !phase) {        // packed bf16 weights: asynchronous, like the A operand
                                 const int nn = it.n0 + prow;
                                 const long long kk = k0 + k8 * 8;
                                 const bool pred = nn < Ntot && kk < Ktot;
@@ -612,6 +644,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
 #pragma unroll 4
                         for (int row = rgo; row < rows_here; row += groups) {
                             const uint4 q = *reinterpret_cast<const uint4*>(sp + row * c_pitch);
+                            if (phase) {    // rows of this sub-problem are the input positions of one parity class
+                                const long long m = m0 + row;
+                                const int w2 = (int)(m % Wp), h2 = (int)((m / Wp) % Hp), n2 = (int)(m / ((long long)Wp * Hp));
+                                *reinterpret_cast<uint4*>((bf16*)p.out + (((long long)n2 * p.H + 2 * h2 + p.ph_h) * p.W +
+                                                                         2 * w2 + p.ph_w) * ldo + col) = q;
+                                continue;
+                            }
                             *reinterpret_cast<uint4*>(outp + (long long)row * ldo) = q;
                             if (do_stats) {
                                 float x[8];
@@ -675,6 +714,11 @@ static bool tc_geom(int mode, const ConvP& p, TcGeom& g, size_t& smem, int& dept
     if (mode == MODE_FWD) { M = (long long)p.N * p.Ho * p.Wo; Nn = p.Cout; K = (long long)kk2 * p.Cin; }
     else if (mode == MODE_DGRAD) { M = (long long)p.N * p.H * p.W; Nn = p.Cin; K = (long long)kk2 * p.Cout; }
     else { M = p.Cout; Nn = kk2 * p.Cin; K = (long long)p.N * p.Ho * p.Wo; }
+    if (mode == MODE_DGRAD && p.phase_mode) {
+        M = (long long)p.N * ((p.H - p.ph_h + 1) / 2) * ((p.W - p.ph_w + 1) / 2);
+        K = (long long)(p.ph_h ? 2 : 1) * (p.ph_w ? 2 : 1) * p.Cout;
+        if (M <= 0) return false;
+    }
     if (p.nchw_in || p.Cin % 8 != 0 || p.Cout % 8 != 0) return false;
     const int nt = (Nn + 127) / 128;
     const int BN = ((Nn + nt - 1) / nt + 15) / 16 * 16;
@@ -743,7 +787,20 @@ static int launch_tc(const ConvP& p, cudaStream_t st, const char* name) {
 }
 
 int conv_fwd_tc(const ConvP& p, cudaStream_t st) { return launch_tc<MODE_FWD>(p, st, "conv_fwd(tcgen05)"); }
-int conv_dgrad_tc(const ConvP& p, cudaStream_t st) { return launch_tc<MODE_DGRAD>(p, st, "conv_dgrad(tcgen05)"); }
+int conv_dgrad_tc(const ConvP& p, cudaStream_t st) {
+    if (p.k == 3 && p.stride == 2 && p.pad == 1 && !p.add && !p.bn_z) {
+        // four dense sub-GEMMs, one per input-position parity class
+        for (int ph = 0; ph < 4; ++ph) {
+            ConvP q = p;
+            q.phase_mode = 1; q.ph_h = ph >> 1; q.ph_w = ph & 1;
+            if ((p.H - q.ph_h + 1) / 2 <= 0 || (p.W - q.ph_w + 1) / 2 <= 0) continue;
+            int r = launch_tc<MODE_DGRAD>(q, st, "conv_dgrad(tcgen05, stride-2 phase)");
+            if (r != 0) return r;
+        }
+        return 0;
+    }
+    return launch_tc<MODE_DGRAD>(p, st, "conv_dgrad(tcgen05)");
+}
 int conv_wgrad_tc(const ConvP& p, cudaStream_t st) { return launch_tc<MODE_WGRAD>(p, st, "conv_wgrad(tcgen05)"); }
 
 }  // namespace mnb

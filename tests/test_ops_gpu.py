@@ -129,6 +129,24 @@ def test_conv_fwd_dgrad_wgrad(case, dtype, impl):
     torch.cuda.synchronize()
     assert rel(nchw(dx), a_.grad + nchw(addd)) < TOL[dtype]
     assert rel(dw, w_.grad) < TOL[dtype]
+    # plain dgrad (no residual / no fused reduction): stride-2 3x3 takes the parity-decomposed tcgen05 path
+    dx3 = torch.full((N, H, W, Cin), 7.0, device="cuda", dtype=tdt(dtype))
+    L.call("mnb_conv_dgrad", P(dzd), P(wd), None, P(dx3), None, None, None, None, N, H, W, Cin, Cout, k, stride, pad,
+           code(dtype), im, stream())
+    torch.cuda.synchronize()
+    assert rel(nchw(dx3), a_.grad) < TOL[dtype]
+    if dtype == "bf16" and im == 0:
+        wpf = torch.empty(Cout * Cin * k * k, device="cuda", dtype=torch.bfloat16)
+        wpd = torch.empty_like(wpf)
+        L.call("mnb_pack_weights", P(wd), P(wpf), P(wpd), Cout, Cin, k, stream())
+        z2 = torch.empty_like(z)
+        L.call("mnb_conv_fwd_packed", P(xd), P(sd), P(td), P(wd), P(wpf), P(bd), P(z2), None, N, H, W, Cin, Cout, k,
+               stride, pad, code(dtype), 0, im, stream())
+        dx4 = torch.empty_like(dx3)
+        L.call("mnb_conv_dgrad_packed", P(dzd), P(wd), P(wpd), None, P(dx4), None, None, None, None, N, H, W, Cin, Cout,
+               k, stride, pad, code(dtype), im, stream())
+        torch.cuda.synchronize()
+        assert torch.equal(z2, z) and torch.equal(dx4, dx3)
     # accumulate semantics
     L.call("mnb_conv_wgrad", P(xd), P(sd), P(td), P(dzd), P(dw), N, H, W, Cin, Cout, k, stride, pad, code(dtype), 0,
            im, stream())
