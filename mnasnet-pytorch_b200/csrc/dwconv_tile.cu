@@ -96,7 +96,7 @@ __device__ __forceinline__ uint4 dw_xform8(uint4 u, const float* s, const float*
 // MODE 0: forward (XF optional, bias, stats)   MODE 1: dgrad (flipped kernel, plain input)   MODE 2: wgrad
 // MODE 3: dgrad + fused BN-backward reduction of the producer block (second, halo-free tile holds its z)
 template <int K, int CB, int MODE>
-__global__ void __launch_bounds__(256, 2) dw_tile_k(DwP p) {
+__global__ void __launch_bounds__(256, (K == 3 ? 3 : 2)) dw_tile_k(DwP p) {
     using Cfg = DwCfg<K, CB>;
     constexpr int P = Cfg::P, NP = Cfg::NP, CW = Cfg::CW, WX = Cfg::WX, TH = Cfg::TH, HC = Cfg::HC, HR = Cfg::HR;
     constexpr int CV8 = Cfg::CV8, NV = Cfg::NV, MAXV = Cfg::MAXV, THT = Cfg::THT, TW = Cfg::TW, PP = Cfg::PP;

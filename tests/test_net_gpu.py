@@ -247,3 +247,31 @@ def test_submodule_forward_backward():
     assert rel(y, r.detach()) < 1e-4
     assert rel(xd.grad, xr.grad) < 1e-3
     assert rel(blk.sequence[0].sequence[0].conv.weight.grad, sd["sequence.0.sequence.0.conv.weight"].grad) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("n,h,w", [(5, 112, 112), (2, 192, 256), (2, 256, 192), (1, 96, 128), (7, 64, 64)])
+def test_shape_polymorphism(n, h, w, dtype):
+    """T4: progressive-resize (112^2 -> 4x4 final maps) and rectangular cluster crops, odd / ragged N."""
+    m = build(dtype)
+    x, t = O.synthetic_batch(n, h, w)
+    out = m(x.cuda())
+    loss = torch.nn.CrossEntropyLoss()(out, t.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    sd32, tr32, logits32, loss32, g32 = oracle_run(n, h, w)
+    tol = 1e-4 if dtype == "fp32" else 2e-2
+    assert abs(loss.item() - loss32.item()) / loss32.item() < tol
+    if dtype == "fp32":
+        assert rel(out, logits32) < 1e-4
+        assert torch.equal(out.argmax(1).cpu(), logits32.argmax(1))
+        for k, p in m.named_parameters():
+            if k.startswith("classifier"):
+                assert rel(p.grad, g32[k]) < 1e-3, k
+    else:
+        assert torch.isfinite(out).all()
+        assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+    # a second shape on the same model re-plans (plan cache keyed by (N,H,W))
+    x2, t2 = O.synthetic_batch(2, 64, 96)
+    out2 = m(x2.cuda())
+    assert out2.shape == (2, 1000) and torch.isfinite(out2).all()
