@@ -204,6 +204,8 @@ def main():
             seq.append([getattr(op, "label", op.name), getattr(op, "detail", ""), op.name])
         seq.append(["xent", "", "mnb_xent_fwd_bwd"])
         for op in plan.bwd:
+            if op.name.startswith("event_"):
+                continue
             seq.append([getattr(op, "label", op.name), getattr(op, "detail", ""), op.name])
             if op.name == "mnb_fc_wgrad":
                 seq.append(["fc_wgrad_bias", "", "mnb_fc_wgrad"])

@@ -69,25 +69,32 @@ class GradSync:
         sched = self.schedule(plan)
         grad = engine.store.grad
         cur = torch.cuda.current_stream()
-        si = 0
         self.works = []
-        for i, op in enumerate(plan.bwd):
-            op(stream)
-            while si < len(sched) and sched[si][0] <= i + 1:
-                self._launch(cur, grad, sched[si][1], sched[si][2])
-                si += 1
-        while si < len(sched):
-            self._launch(cur, grad, sched[si][1], sched[si][2])
-            si += 1
+        state = {"si": 0}
 
-    def _launch(self, cur, grad, lo, hi):
+        def after(i):
+            while state["si"] < len(sched) and sched[state["si"]][0] <= i + 1:
+                self._launch(cur, grad, sched[state["si"]][1], sched[state["si"]][2], plan, engine)
+                state["si"] += 1
+        plan.run(plan.bwd, stream, after_op=after)
+        while state["si"] < len(sched):
+            self._launch(cur, grad, sched[state["si"]][1], sched[state["si"]][2], plan, engine)
+            state["si"] += 1
+
+    def _launch(self, cur, grad, lo, hi, plan=None, engine=None):
         if self.world == 1:
             return
         if self.overlap:
             ev = torch.cuda.Event()
             ev.record(cur)
+            ev2 = None
+            if engine is not None and getattr(engine, "wgrad_slack", 0) > 0:
+                ev2 = torch.cuda.Event()              # weight gradients are written on the engine's side stream
+                ev2.record(engine.side_stream)
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
+                if ev2 is not None:
+                    self.comm_stream.wait_event(ev2)
                 self.works.append(dist.all_reduce(grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
                                                   async_op=True))
         else:

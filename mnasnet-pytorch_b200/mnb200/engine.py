@@ -169,6 +169,9 @@ class Plan:
         self.generation = 0
         self.last_write = {}
         self.packed = {}
+        self.n_events = 0
+        self.side_last = None
+        self.events = None
         self._arena_f, self._arena_d = [], []   # (numel) requests
         self._build()
 
@@ -380,10 +383,21 @@ class Plan:
         maxel = 1
         for a in self.apps:
             maxel = max(maxel, a.inp.M * a.inp.C if not a.inp.nchw else 1, int(a.m) * a.Cout)
-        pool = [torch.empty(maxel, device=self.dev, dtype=self.tdtype) for _ in range(4)]
+        # 4 buffers are live at most on the main chain; the extra ones give the weight-gradient kernels (side
+        # stream, off the critical path) time to finish before their dZ operand is recycled
+        pool = [torch.empty(maxel, device=self.dev, dtype=self.tdtype) for _ in range(4 + eng.wgrad_slack)]
         self.keep += pool
         free = list(pool)
         ops = self.bwd
+        pending = {}                       # id(buffer) -> event id of the side-stream wgrad still reading it
+        side = eng.wgrad_slack > 0
+
+        def take():
+            b = free.pop(0)                # FIFO: the buffer released longest ago
+            ev = pending.pop(id(b), None)
+            if ev is not None:
+                ops.append(_EventOp("wait", ev, 0))
+            return b
         net = getattr(eng.module, "_mnb", None) == "net"
         if net:
             # head backward
@@ -399,11 +413,11 @@ class Plan:
                 relu_ref = r["x"] if (i > 0 and self.head[i - 1]["relu"]) else None
                 self._op(ops, "mnb_fc_dgrad", g, lin.weight, maskp, ms, relu_ref, dx, self.N, r["K"], r["O"])
                 g = dx
-            gbuf = free.pop()
+            gbuf = take()
             hi = self.head_in
             self._op(ops, "mnb_gap_bwd", g, gbuf, self.N, hi.H * hi.W, hi.C, self.code)
         else:
-            gbuf = free.pop()
+            gbuf = take()
             self.sub_dout = gbuf          # filled from the NCHW grad_output at run time
         held = []                          # stack of residual-skip gradients
         for idx in range(len(self.tape) - 1, -1, -1):
@@ -422,7 +436,7 @@ class Plan:
                 conv, bn = a.cb.conv, a.cb.bn
                 M, C = int(a.m), a.Cout
                 self._cur_detail = f"{a.inp.H}x{a.inp.W} {a.inp.C}->{a.Cout} k{a.k}s{a.stride}"
-                dz = free.pop()
+                dz = take()
                 if not a.reduce_fused:     # else: done in the epilogue of the dgrad that produced gbuf
                     self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
                              nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
@@ -436,6 +450,10 @@ class Plan:
                 r = a.inp
                 x_t = r.t if not r.nchw else _InputPtr(self)
                 layout = _lib.LAYOUT_NCHW_F32 if r.nchw else _lib.LAYOUT_NHWC
+                if side:                   # fork: the side stream may start once dZ is complete
+                    ev_dz = self._new_event()
+                    ops.append(_EventOp("record", ev_dz, 0))
+                    ops.append(_EventOp("wait", ev_dz, 1))
                 if a.kind == "dense":
                     self._op(ops, "mnb_conv_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W,
                              r.C, C, a.k, a.stride, a.pad, self.code, layout, eng.impl,
@@ -443,8 +461,14 @@ class Plan:
                 else:
                     self._op(ops, "mnb_dw_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W, r.C,
                              a.k, self.code, nbytes=a.in_bytes + a.out_bytes, label=a.label + "_wgrad")
+                if side:
+                    ops[-1].stream_id = 1
+                    ev_w = self._new_event()
+                    ops.append(_EventOp("record", ev_w, 1))
+                    pending[id(dz)] = ev_w
+                    self.side_last = ev_w
                 if a.need_dgrad:
-                    dx = free.pop()
+                    dx = take()
                     # the first conv of a residual block adds the skip gradient (dY) into its dgrad output
                     add = None
                     if idx > 0 and self.tape[idx - 1][0] == "res_begin":
@@ -471,6 +495,12 @@ class Plan:
                     free.append(dz)
                     gbuf = None
         self.sub_din = gbuf
+        if side and getattr(self, "side_last", None) is not None:
+            ops.append(_EventOp("wait", self.side_last, 0))      # join: optimizer / caller see all weight grads
+
+    def _new_event(self):
+        self.n_events += 1
+        return self.n_events - 1
 
     # ---- op plumbing -----------------------------------------------------------------------------------
     def _op(self, ops, name, *args, nbytes=0, label=None):
@@ -489,17 +519,34 @@ class Plan:
                 conv.append(a)
         op = _Op(name, fn, conv, self)
         op.nbytes, op.label = nbytes, label or name
+        op.stream_id = 0
         op.detail = getattr(self, "_cur_detail", "")
         ops.append(op)
 
-    def run(self, ops, stream):
+    def run(self, ops, stream, after_op=None):
         prof = self.eng.profile
         if prof is None:
-            for op in ops:
-                op(stream)
+            if self.n_events and self.events is None:
+                self.events = [torch.cuda.Event() for _ in range(self.n_events)]
+            main = torch.cuda.current_stream()
+            side = self.eng.side_stream
+            side_ptr = side.cuda_stream
+            for i, op in enumerate(ops):
+                if op.__class__ is _EventOp:
+                    st = main if op.stream_id == 0 else side
+                    if op.kind == "record":
+                        self.events[op.ev].record(st)
+                    else:
+                        st.wait_event(self.events[op.ev])
+                else:
+                    op(stream if getattr(op, "stream_id", 0) == 0 else side_ptr)
+                if after_op is not None:
+                    after_op(i)
             return
         cur = torch.cuda.current_stream()
         for op in ops:          # per-launch CUDA-event timing on the launching stream (bench.py roofline pass)
+            if op.__class__ is _EventOp:
+                continue        # profiling pass is single-stream: no cross-stream dependencies needed
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(cur)
             op(stream)
@@ -603,6 +650,16 @@ class _Op:
             check(rc, self.name)
 
 
+class _EventOp:
+    """Cross-stream dependency inside a program: record / wait of plan event `ev` on stream 0 (main) or 1 (the
+    weight-gradient side stream)."""
+    __slots__ = ("kind", "ev", "stream_id", "name")
+
+    def __init__(self, kind, ev, stream_id):
+        self.kind, self.ev, self.stream_id = kind, ev, stream_id
+        self.name = "event_" + kind
+
+
 class _DropoutOp:
     """Generates a dropout keep-mask unless dropout is off or masks were injected for this call."""
 
@@ -640,6 +697,8 @@ class Engine:
         self.grad_hook = None          # DDP: callable(engine, stage) invoked while backward is enqueued
         self.graphs = {}
         self.world_size = 1
+        self.wgrad_slack = 4           # extra scratch buffers = how far weight-gradient kernels may trail
+        self.side_stream = torch.cuda.Stream(device=self.device)
         self.fuse_bn_reduce = False    # BN-backward reductions in the producing dgrad epilogue (tested; off:
                                        # the dgrad epilogues are the bottleneck, the separate kernel is faster)
         self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
@@ -795,6 +854,8 @@ class Engine:
         plan = self.plan(N, H, W)
         n = 0
         for op in plan.fwd + plan.bwd:
+            if op.__class__ is _EventOp:
+                continue
             n += 2 if getattr(op, "name", "") == "mnb_fc_wgrad" else 1
         return n + 3          # xent, counter_inc, adam
 
