@@ -69,7 +69,7 @@ struct DwCfg {
     static constexpr int CW = 32 / NP;              // output column groups per warp (each group = 2 columns)
     static constexpr int WX = 8 / CW;               // warps along W  (tile width = WX*CW*2 = 16)
     static constexpr int WY = CW;                   // warps along H
-    static constexpr int TH = 8;                    // rows per thread
+    static constexpr int TH = 7;                    // rows per thread (every MNASNet-224 map height is a multiple of 7)
     static constexpr int TW = 16;                   // tile width
     static constexpr int THT = WY * TH;             // tile height
     static constexpr int HR = THT + K - 1, HC = TW + K - 1;
