@@ -96,6 +96,15 @@ int mnb_bn_finalize(const double* stats, const float* gamma, const float* beta, 
 /* eval mode: scale/shift from running stats */
 int mnb_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float* scale, float* shift, int C, float eps, void* stream);
+/* Folded conv bias (conv_bias != NULL): the statistics were taken over z' = conv(x) WITHOUT its bias b (train-mode
+ * BatchNorm cancels b exactly, so the conv kernels can skip the add).  scale/shift/save_mean refer to z';
+ * running_mean tracks mean(z') + b as the reference's nn.Conv2d(bias=True) -> nn.BatchNorm2d would. */
+int mnb_bn_finalize_fb(const double* stats, const float* gamma, const float* beta, const float* conv_bias,
+                       float* running_mean, float* running_var, long long* num_batches_tracked, float* scale,
+                       float* shift, float* save_mean, float* save_invstd, int C, double m, float eps,
+                       float momentum, void* stream);
+int mnb_bn_eval_coeffs_fb(const float* gamma, const float* beta, const float* conv_bias, const float* running_mean,
+                          const float* running_var, float* scale, float* shift, int C, float eps, void* stream);
 /* y = (residual ? residual : 0) + max(scale*z+shift, 0)     (BN-apply + ReLU + MBConv_block skip add) */
 int mnb_bn_relu_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y,
                       long long M, int C, int dtype, void* stream);
@@ -106,6 +115,11 @@ int mnb_bn_bwd_reduce(const void* dA, const void* z, const float* scale, const f
 int mnb_bn_bwd_finalize(const double* sums, const float* scale, const float* save_mean,
                         const float* save_invstd, float* dgamma, float* dbeta, float* dbias, float* coef, int C,
                         double m, void* stream);
+/* bn_bwd_finalize + bn_bwd_apply in one launch: every CTA derives a,b,c for its channels from `sums`; dgamma /
+ * dbeta / dbias (nullable) are accumulated once. */
+int mnb_bn_bwd_apply_fused(const void* dA, const void* z, const float* scale, const float* shift, const double* sums,
+                           const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                           float* dbias, void* dZ, long long M, int C, double m, int dtype, void* stream);
 /* dZ = a*G + b*z + c  (materialised) */
 int mnb_bn_bwd_apply(const void* dA, const void* z, const float* scale, const float* shift, const float* coef,
                      void* dZ, long long M, int C, int dtype, void* stream);

@@ -71,7 +71,8 @@ __device__ __forceinline__ void flush_channel_partials(float (&acc)[NQ][8], doub
 // BN finalize / eval coefficients
 // ---------------------------------------------------------------------------------------------------
 __global__ void bn_finalize_k(const double* __restrict__ stats, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, float* running_mean, float* running_var,
+                              const float* __restrict__ beta, const float* __restrict__ conv_bias,
+                              float* running_mean, float* running_var,
                               long long* nbt, float* scale, float* shift, float* save_mean, float* save_invstd,
                               int C, double m, float eps, float momentum) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,18 +89,19 @@ __global__ void bn_finalize_k(const double* __restrict__ stats, const float* __r
     if (save_invstd) save_invstd[c] = (float)invstd;
     if (running_mean) {
         double unb = m > 1 ? var * m / (m - 1) : var;
-        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+        const double mb = mean + (conv_bias ? (double)conv_bias[c] : 0.0);      // folded conv bias
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mb);
         running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
     }
 }
 
-__global__ void bn_eval_coeffs_k(const float* gamma, const float* beta, const float* rm, const float* rv,
-                                 float* scale, float* shift, int C, float eps) {
+__global__ void bn_eval_coeffs_k(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
+                                 const float* rv, float* scale, float* shift, int C, float eps) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s = gamma[c] / sqrtf(rv[c] + eps);
     scale[c] = s;
-    shift[c] = beta[c] - rm[c] * s;
+    shift[c] = beta[c] - (rm[c] - (conv_bias ? conv_bias[c] : 0.f)) * s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -205,6 +207,65 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_k(const T* __restrict__ dA, 
     load8(coef + c0, ca);
     load8(coef + C + c0, cb);
     load8(coef + 2 * C + c0, cc);
+    const long long stride = (long long)gridDim.y * blockDim.y;
+    long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    for (; r + stride < M; r += 2 * stride) {
+        float a0[8], z0[8], a1[8], z1[8];
+        load8(dA + r * C + c0, a0);
+        load8(z + r * C + c0, z0);
+        load8(dA + (r + stride) * C + c0, a1);
+        load8(z + (r + stride) * C + c0, z1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float g0 = fmaf(s[i], z0[i], t[i]) > 0.f ? a0[i] : 0.f;
+            const float g1 = fmaf(s[i], z1[i], t[i]) > 0.f ? a1[i] : 0.f;
+            a0[i] = fmaf(ca[i], g0, fmaf(cb[i], z0[i], cc[i]));
+            a1[i] = fmaf(ca[i], g1, fmaf(cb[i], z1[i], cc[i]));
+        }
+        store8(dZ + r * C + c0, a0);
+        store8(dZ + (r + stride) * C + c0, a1);
+    }
+    for (; r < M; r += stride) {
+        float a0[8], z0[8];
+        load8(dA + r * C + c0, a0);
+        load8(z + r * C + c0, z0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float g0 = fmaf(s[i], z0[i], t[i]) > 0.f ? a0[i] : 0.f;
+            a0[i] = fmaf(ca[i], g0, fmaf(cb[i], z0[i], cc[i]));
+        }
+        store8(dZ + r * C + c0, a0);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_fused_k(const T* __restrict__ dA, const T* __restrict__ z,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const double* __restrict__ sums,
+                                                            const float* __restrict__ save_mean,
+                                                            const float* __restrict__ save_invstd, float* dgamma,
+                                                            float* dbeta, float* dbias, T* __restrict__ dZ, long long M,
+                                                            int C, double m) {
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    float s[8], t[8], ca[8], cb[8], cc[8];
+    load8(scale + c0, s);
+    load8(shift + c0, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {       // the per-channel work of bn_bwd_finalize, redundantly per CTA
+        const int c = c0 + i;
+        const double sg = sums[c], sgz = sums[C + c];
+        const double mean = save_mean[c], invstd = save_invstd[c], sc = s[i];
+        const double dga = invstd * (sgz - mean * sg);
+        const double b = -sc * invstd * dga / m;
+        const double c3 = -sc * sg / m - b * mean;
+        ca[i] = (float)sc; cb[i] = (float)b; cc[i] = (float)c3;
+        if (blockIdx.y == 0 && threadIdx.y == 0) {
+            if (dgamma) dgamma[c] += (float)dga;
+            if (dbeta) dbeta[c] += (float)sg;
+            if (dbias) dbias[c] += (float)(sc * sg + b * mean * m + c3 * m);
+        }
+    }
     const long long stride = (long long)gridDim.y * blockDim.y;
     long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
     for (; r + stride < M; r += 2 * stride) {
@@ -513,22 +574,48 @@ int mnb_device_is_sm100(void) {
     return major == 10;
 }
 
+int mnb_bn_finalize_fb(const double* stats, const float* gamma, const float* beta, const float* conv_bias,
+                       float* running_mean, float* running_var, long long* nbt, float* scale, float* shift,
+                       float* save_mean, float* save_invstd, int C, double m, float eps, float momentum, void* stream) {
+    MNB_REQUIRE(C > 0 && m > 0, "bn_finalize: bad C/m");
+    bn_finalize_k<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, gamma, beta, conv_bias, running_mean,
+                                                                      running_var, nbt, scale, shift, save_mean,
+                                                                      save_invstd, C, m, eps, momentum);
+    MNB_LAUNCH_CHECK("bn_finalize");
+    return 0;
+}
+
 int mnb_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, long long* nbt, float* scale, float* shift, float* save_mean,
                     float* save_invstd, int C, double m, float eps, float momentum, void* stream) {
-    MNB_REQUIRE(C > 0 && m > 0, "bn_finalize: bad C/m");
-    bn_finalize_k<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, gamma, beta, running_mean, running_var,
-                                                                      nbt, scale, shift, save_mean, save_invstd, C,
-                                                                      m, eps, momentum);
-    MNB_LAUNCH_CHECK("bn_finalize");
+    return mnb_bn_finalize_fb(stats, gamma, beta, nullptr, running_mean, running_var, nbt, scale, shift, save_mean,
+                              save_invstd, C, m, eps, momentum, stream);
+}
+
+int mnb_bn_eval_coeffs_fb(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
+                          const float* rv, float* scale, float* shift, int C, float eps, void* stream) {
+    MNB_REQUIRE(C > 0, "bn_eval_coeffs: bad C");
+    bn_eval_coeffs_k<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, conv_bias, rm, rv, scale, shift, C,
+                                                                         eps);
+    MNB_LAUNCH_CHECK("bn_eval_coeffs");
     return 0;
 }
 
 int mnb_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, const float* rv, float* scale,
                        float* shift, int C, float eps, void* stream) {
-    MNB_REQUIRE(C > 0, "bn_eval_coeffs: bad C");
-    bn_eval_coeffs_k<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, rm, rv, scale, shift, C, eps);
-    MNB_LAUNCH_CHECK("bn_eval_coeffs");
+    return mnb_bn_eval_coeffs_fb(gamma, beta, nullptr, rm, rv, scale, shift, C, eps, stream);
+}
+
+int mnb_bn_bwd_apply_fused(const void* dA, const void* z, const float* scale, const float* shift, const double* sums,
+                           const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* dbias,
+                           void* dZ, long long M, int C, double m, int dtype, void* stream) {
+    MNB_REQUIRE(C % 8 == 0 && M > 0 && m > 0, "bn_bwd_apply_fused: bad shape");
+    ColGeom g = col_geom(M, C, 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) bn_bwd_apply_fused_k<float><<<g.grid, g.block, 0, st>>>((const float*)dA, (const float*)z, scale, shift, sums, save_mean, save_invstd, dgamma, dbeta, dbias, (float*)dZ, M, C, m);
+    else if (dtype == MNB_BF16) bn_bwd_apply_fused_k<bf16><<<g.grid, g.block, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, sums, save_mean, save_invstd, dgamma, dbeta, dbias, (bf16*)dZ, M, C, m);
+    else MNB_REQUIRE(false, "bn_bwd_apply_fused: bad dtype");
+    MNB_LAUNCH_CHECK("bn_bwd_apply_fused");
     return 0;
 }
 

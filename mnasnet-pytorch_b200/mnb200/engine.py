@@ -296,18 +296,19 @@ class Plan:
         for ops, train in ((self.fwd, True), (self.fwd_eval, False)):
             st = a.stats if train else None
             if a.kind == "dense":
-                self._op(ops, "mnb_conv_fwd_packed", x_t, ref.scale, ref.shift, conv.weight, wpk[0], conv.bias, a.z, st,
+                self._op(ops, "mnb_conv_fwd_packed", x_t, ref.scale, ref.shift, conv.weight, wpk[0], None, a.z, st,
                          ref.N, ref.H, ref.W, cin, cout, k, stride, pad, self.code, layout, eng.impl,
                          nbytes=in_b + out_b, label=a.label + "_fwd")
             else:
-                self._op(ops, "mnb_dw_fwd", x_t, ref.scale, ref.shift, conv.weight, conv.bias, a.z, st,
+                self._op(ops, "mnb_dw_fwd", x_t, ref.scale, ref.shift, conv.weight, None, a.z, st,
                          ref.N, ref.H, ref.W, cin, k, self.code, nbytes=in_b + out_b, label=a.label + "_fwd")
             if train:
-                self._op(ops, "mnb_bn_finalize", a.stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                # the conv bias is folded into BN (train-mode BN cancels it): Z is stored without it
+                self._op(ops, "mnb_bn_finalize_fb", a.stats, bn.weight, bn.bias, conv.bias, bn.running_mean, bn.running_var,
                          bn.num_batches_tracked, a.scale, a.shift, a.mean, a.invstd, cout, a.m,
                          float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1))
             else:
-                self._op(ops, "mnb_bn_eval_coeffs", bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                self._op(ops, "mnb_bn_eval_coeffs_fb", bn.weight, bn.bias, conv.bias, bn.running_mean, bn.running_var,
                          a.scale, a.shift, cout, float(bn.eps))
         a.index, a.reduce_fused = len(self.apps), False
         self.apps.append(a)
@@ -440,9 +441,8 @@ class Plan:
                 if not a.reduce_fused:     # else: done in the epilogue of the dgrad that produced gbuf
                     self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
                              nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
-                self._op(ops, "mnb_bn_bwd_finalize", a.sums, a.scale, a.mean, a.invstd, _G(bn.weight),
-                         _G(bn.bias), _G(conv.bias), a.coef, C, a.m)
-                self._op(ops, "mnb_bn_bwd_apply", gbuf, a.z, a.scale, a.shift, a.coef, dz, M, C, self.code,
+                self._op(ops, "mnb_bn_bwd_apply_fused", gbuf, a.z, a.scale, a.shift, a.sums, a.mean, a.invstd,
+                         _G(bn.weight), _G(bn.bias), _G(conv.bias), dz, M, C, a.m, self.code,
                          nbytes=3 * a.out_bytes, label="bn_bwd_apply")
                 in_held = any(gbuf is h for h in held)
                 if not in_held:

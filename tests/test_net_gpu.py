@@ -275,3 +275,32 @@ def test_shape_polymorphism(n, h, w, dtype):
     x2, t2 = O.synthetic_batch(2, 64, 96)
     out2 = m(x2.cuda())
     assert out2.shape == (2, 1000) and torch.isfinite(out2).all()
+
+
+def test_nonzero_conv_bias_is_folded_exactly():
+    """Reference checkpoints carry non-zero conv biases; the CUDA path stores Z without the bias and folds it
+    into BN finalize / eval coefficients.  Train logits, running_mean and eval logits must still match."""
+    torch.manual_seed(42)
+    sd = O.init_state_dict()
+    g = torch.Generator().manual_seed(3)
+    seen = set()
+    for k, v in sd.items():
+        if k.endswith("conv.bias") and id(v) not in seen:
+            seen.add(id(v))
+            v.copy_(torch.randn(v.shape, generator=g) * 0.2)
+    m = build("fp32")
+    m.load_state_dict(sd)
+    x, t = O.synthetic_batch(3, 96, 128)
+    out = m(x.cuda())
+    with torch.no_grad():
+        ref = O.forward(sd, x, True, dropout_masks="off")
+    assert rel(out, ref) < 1e-4
+    msd = m.state_dict()
+    for k in sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel(msd[k], sd[k]) < 1e-4, k
+    m.eval()
+    with torch.no_grad():
+        ev = m(x.cuda())
+        ref_ev = O.forward(sd, x, False)
+    assert rel(ev, ref_ev) < 1e-4

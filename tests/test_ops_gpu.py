@@ -292,6 +292,28 @@ def test_batchnorm_forward_backward(shape, dtype):
     assert rel(db, b_.grad) < 1e-4
     assert rel(nchw(dZ), z_.grad) < TOL[dtype]
     assert dbias.abs().max().item() <= 1e-5 * max(1.0, z_.grad.abs().sum().item())
+    # finalize + apply in one launch
+    dg2, db2, dbias2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dZ2 = torch.empty_like(dZ)
+    L.call("mnb_bn_bwd_apply_fused", P(dAd), P(zd), P(vec[0]), P(vec[1]), P(sums), P(vec[2]), P(vec[3]), P(dg2), P(db2),
+           P(dbias2), P(dZ2), M, C, float(M), code(dtype), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dZ2, dZ) and torch.equal(dg2, dg) and torch.equal(db2, db)
+    # folded conv bias: statistics of z - b with the bias handed to finalize give the same activation / buffers
+    cbias = (torch.randn(C, generator=g) * 0.3)
+    zb = nhwc(z - cbias.double()[None, :, None, None], "fp32")
+    zbn = nchw(zb)
+    stats_b = torch.stack([zbn.sum(dim=(0, 2, 3)), (zbn * zbn).sum(dim=(0, 2, 3))]).reshape(-1).cuda()
+    rm2, rv2 = rm.clone().cuda(), rv.clone().cuda()
+    vec2 = torch.zeros(4, C, device="cuda")
+    L.call("mnb_bn_finalize_fb", P(stats_b), P(gd), P(bd), P(cbias.cuda()), P(rm2), P(rv2), None, P(vec2[0]),
+           P(vec2[1]), P(vec2[2]), P(vec2[3]), C, float(M), 1e-5, 0.1, stream())
+    torch.cuda.synchronize()
+    act_a = torch.relu(vec[0].cpu().double()[None, :, None, None] * z + vec[1].cpu().double()[None, :, None, None])
+    act_b = torch.relu(vec2[0].cpu().double()[None, :, None, None] * zbn + vec2[1].cpu().double()[None, :, None, None])
+    assert rel(act_b, act_a) < 1e-4
+    torch.testing.assert_close(rm2, rmd, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rv2, rvd, rtol=1e-4, atol=1e-5)
     # eval coefficients
     sc, sh = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     L.call("mnb_bn_eval_coeffs", P(gd), P(bd), P(rmd), P(rvd), P(sc), P(sh), C, 1e-5, stream())
