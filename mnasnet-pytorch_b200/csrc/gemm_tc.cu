@@ -203,7 +203,7 @@ struct ChunkIt {
     bool row_ok;
 };
 
-template <int MODE, int D>
+template <int MODE, int D, bool ONE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     if (MODE == MODE_FWD) { Mtot = (long long)p.N * p.Ho * p.Wo; Ntot = p.Cout; Ktot = (long long)kk2 * p.Cin; }
     else if (MODE == MODE_DGRAD) { Mtot = (long long)p.N * p.H * p.W; Ntot = p.Cin; Ktot = (long long)kk2 * p.Cout; }
     else { Mtot = p.Cout; Ntot = kk2 * p.Cin; Ktot = (long long)p.N * p.Ho * p.Wo; }
-    const bool phase = (MODE == MODE_DGRAD) && p.phase_mode;
+    const bool phase = (MODE == MODE_DGRAD) && !ONE && p.phase_mode;
     const int Hp = phase ? (p.H - p.ph_h + 1) / 2 : p.H, Wp = phase ? (p.W - p.ph_w + 1) / 2 : p.W;
     if (phase) { Mtot = (long long)p.N * Hp * Wp; Ktot = (long long)(p.ph_h ? 2 : 1) * (p.ph_w ? 2 : 1) * p.Cout; }
     const int total_chunks = (int)((Ktot + kc - 1) / kc);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const bool is1x1 = (kk2 == 1 && p.stride == 1);
+    constexpr bool is1x1 = ONE;       // 1x1 stride-1: compile-time, the im2col / phase code drops out
 
     if (warp < 8) {
         // =========================== PRODUCERS (8 warps) ===========================
@@ -744,11 +744,11 @@ static bool tc_geom(int mode, const ConvP& p, TcGeom& g, size_t& smem, int& dept
     return smem <= 227 * 1024;
 }
 
-template <int MODE, int D>
+template <int MODE, int D, bool ONE>
 static int launch_tc_d(const ConvP& p, TcGeom& g, size_t smem, cudaStream_t st, const char* name) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_k<MODE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_k<MODE, D, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
@@ -770,7 +770,7 @@ static int launch_tc_d(const ConvP& p, TcGeom& g, size_t smem, cudaStream_t st, 
         grid = tiles < slots ? tiles : slots / g.n_tiles * g.n_tiles;
         if (grid < g.n_tiles) grid = g.n_tiles;
     }
-    conv_tc_k<MODE, D><<<(unsigned)grid, TC_THREADS, smem, st>>>(p, g);
+    conv_tc_k<MODE, D, ONE><<<(unsigned)grid, TC_THREADS, smem, st>>>(p, g);
     MNB_LAUNCH_CHECK(name);
     return 0;
 }
@@ -782,8 +782,9 @@ static int launch_tc(const ConvP& p, cudaStream_t st, const char* name) {
     size_t smem;
     int depth;
     if (!tc_geom(MODE, p, g, smem, depth)) { set_error("%s: shape not covered", name); return MNB_ERR_UNSUPPORTED; }
-    if (depth == 8) return launch_tc_d<MODE, 8>(p, g, smem, st, name);
-    return launch_tc_d<MODE, 3>(p, g, smem, st, name);
+    const bool one = (p.k == 1 && p.stride == 1);
+    if (depth == 8) return one ? launch_tc_d<MODE, 8, true>(p, g, smem, st, name) : launch_tc_d<MODE, 8, false>(p, g, smem, st, name);
+    return one ? launch_tc_d<MODE, 3, true>(p, g, smem, st, name) : launch_tc_d<MODE, 3, false>(p, g, smem, st, name);
 }
 
 int conv_fwd_tc(const ConvP& p, cudaStream_t st) { return launch_tc<MODE_FWD>(p, st, "conv_fwd(tcgen05)"); }
