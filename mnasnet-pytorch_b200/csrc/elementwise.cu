@@ -147,19 +147,22 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_k(const T* __restrict__ dA,
     for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
     const long long stride = (long long)gridDim.y * blockDim.y;
     long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-    for (; r + stride < M; r += 2 * stride) {
-        float a0[8], z0[8], a1[8], z1[8];
-        load8(dA + r * C + c0, a0);
-        load8(z + r * C + c0, z0);
-        load8(dA + (r + stride) * C + c0, a1);
-        load8(z + (r + stride) * C + c0, z1);
+    // 4 rows (8 x 16-byte loads) in flight per thread: the kernel runs with few, fat CTAs (see the launcher)
+    for (; r + 3 * stride < M; r += 4 * stride) {
+        float a[4][8], zz[4][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float g0 = fmaf(s[i], z0[i], t[i]) > 0.f ? a0[i] : 0.f;
-            float g1 = fmaf(s[i], z1[i], t[i]) > 0.f ? a1[i] : 0.f;
-            acc[0][i] += g0 + g1;
-            acc[1][i] = fmaf(g0, z0[i], fmaf(g1, z1[i], acc[1][i]));
+        for (int u = 0; u < 4; ++u) {
+            load8(dA + (r + u * stride) * C + c0, a[u]);
+            load8(z + (r + u * stride) * C + c0, zz[u]);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float g = fmaf(s[i], zz[u][i], t[i]) > 0.f ? a[u][i] : 0.f;
+                acc[0][i] += g;
+                acc[1][i] = fmaf(g, zz[u][i], acc[1][i]);
+            }
     }
     for (; r < M; r += stride) {
         float a0[8], z0[8];
@@ -639,7 +642,7 @@ int mnb_bn_bwd_reduce(const void* dA, const void* z, const float* scale, const f
                       long long M, int C, int dtype, void* stream) {
     MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_bwd_reduce: C %% 8 != 0 or M <= 0");
     // few, fat CTAs: every CTA ends with one fp64 atomic per channel and same-address atomics serialise in L2
-    ColGeom g = col_geom(M, C, 2);
+    ColGeom g = col_geom(M, C, 3);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MNB_F32) bn_bwd_reduce_k<float><<<g.grid, g.block, 0, st>>>((const float*)dA, (const float*)z, scale, shift, sums, M, C);
     else if (dtype == MNB_BF16) bn_bwd_reduce_k<bf16><<<g.grid, g.block, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, sums, M, C);
