@@ -105,7 +105,12 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 2)) dw_tile_k(DwP p) {
     constexpr bool DGRAD = (MODE == 1 || MODE == 3);
     constexpr int STAGE = Cfg::TILE_BYTES + (SIDE ? Cfg::DZ_BYTES : 0);
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int cbase = blockIdx.y * CB;
+    // 1-D grid, channel block fastest: the CTAs that own the different channel blocks of the SAME spatial tile
+    // are co-scheduled and walk the tiles in the same order, so a pixel's bytes are fetched from DRAM once (as
+    // whole bursts) and the sibling CTAs hit in L2
+    const int cblocks = p.C / CB;
+    const int cbase = (blockIdx.x % cblocks) * CB;
+    const int slot = blockIdx.x / cblocks, nslots = gridDim.x / cblocks;
     const int cp = lane % NP, csub = lane / NP;
     const bool lane_on = csub < CW;
     const int wx = wid % WX, wy = wid / WX;
@@ -200,12 +205,12 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 2)) dw_tile_k(DwP p) {
         return mask;
     };
 
-    long long item = blockIdx.x;
+    long long item = slot;
     int stage = 0;
     unsigned mask = 0, mask_next = 0;
     if (item < p.items) mask = issue(item, 0);
-    for (; item < p.items; item += gridDim.x) {
-        const long long nxt = item + gridDim.x;
+    for (; item < p.items; item += nslots) {
+        const long long nxt = item + nslots;
         if (nxt < p.items) {
             mask_next = issue(nxt, stage ^ 1);
             dcp_wait<1>();
@@ -384,7 +389,7 @@ static int launch_dw_tile(DwP p, cudaStream_t st, const char* name) {
     long long gx = ((long long)num_sms() * per_sm + cblocks - 1) / cblocks;
     if (gx > p.items) gx = p.items;
     if (gx < 1) gx = 1;
-    dim3 grid((unsigned)gx, (unsigned)cblocks);
+    dim3 grid((unsigned)(gx * cblocks));
     dw_tile_k<K, CB, MODE><<<grid, 256, smem, st>>>(p);
     MNB_LAUNCH_CHECK(name);
     return 0;
