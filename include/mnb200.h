@@ -145,6 +145,22 @@ int mnb_fc_dgrad(const float* dy, const float* w, const unsigned char* mask, flo
 int mnb_fc_wgrad(const float* x, const unsigned char* mask, float mask_scale, const float* dy, float* dw,
                  float* db, int N, int K, int O, void* stream);
 
+/* ---- classifier on the tensor pipe (bf16 mode; nn.Linear, classifiers.py:56-89) -------------------------------
+ * xb[i] = bf16( x[i] * (mask ? mask[i]*mask_scale : 1) )      operand prep (dropout folded in) */
+int mnb_fc_prep_bf16(const float* x, const unsigned char* mask, float mask_scale, void* xb, long long n, void* stream);
+/* y[n,o] = b[o] + sum_k xb[n,k]*w[o,k] (fp32 out, optional ReLU) as a tcgen05 GEMM; wpk = mnb_pack_weights(w, O, K, 1)
+ * forward packing (bf16 [O][K]).  Requires K % 8 == 0. */
+int mnb_fc_fwd_tc(const void* xb, const float* w, const void* wpk_fwd, const float* b, float* y, int relu_out, int N,
+                  int K, int O, void* stream);
+/* dx[n,k] = sum_o dyb[n,o]*w[o,k] (fp32 out, ungated) ; wpk_dgrad = bf16 [K][O].  Requires K % 8 == 0, O % 8 == 0. */
+int mnb_fc_dgrad_tc(const void* dyb, const float* w, const void* wpk_dgrad, float* dx, int N, int K, int O,
+                    void* stream);
+/* dx[i] *= mask[i]*mask_scale * (relu_ref ? relu_ref[i] > 0 : 1)   (dropout / ReLU backward of the FC input) */
+int mnb_fc_gate(float* dx, const unsigned char* mask, float mask_scale, const float* relu_ref, long long n,
+                void* stream);
+/* db[o] += sum_n dy[n,o] */
+int mnb_fc_bias_grad(const float* dy, float* db, int N, int O, void* stream);
+
 /* ---- loss : nn.CrossEntropyLoss(mean), train.py:277,435 --------------------------------------------------
  * loss[0] += mean_n( -log softmax(logits_n)[target_n] ) (caller zeroes loss);
  * dlogits (nullable) = (softmax - onehot) * grad_scale / N */

@@ -26,6 +26,8 @@ struct ConvP {
     // stride-2 3x3 backward-data, decomposed by input-position parity (ph_h, ph_w): only the taps with
     // (h+1-kh) and (w+1-kw) even contribute -> 4 dense sub-problems with 1/2/2/4 taps instead of 9 mostly-zero ones
     int phase_mode, ph_h, ph_w;
+    int out_f32;          // fwd/dgrad: write fp32 rows straight from the accumulator (classifier GEMMs)
+    int relu_out;         // with out_f32: apply ReLU
     long long kchunk;     // wgrad: positions per blockIdx.z
 };
 

@@ -406,6 +406,27 @@ int mnb_conv_dgrad_packed(const void* dz, const float* w, const void* wpk, const
     return conv_dgrad_simt(p, dtype, (cudaStream_t)stream);
 }
 
+int mnb_fc_fwd_tc(const void* xb, const float* w, const void* wpk, const float* b, float* y, int relu_out, int N, int K,
+                  int O, void* stream) {
+    MNB_REQUIRE(N > 0 && K > 0 && O > 0 && K % 8 == 0, "fc_fwd_tc: K=%d must be a positive multiple of 8", K);
+    ConvP p = {};
+    p.x = xb; p.w = w; p.wpk = wpk; p.bias = b; p.out = y; p.out_f32 = 1; p.relu_out = relu_out;
+    p.N = N; p.H = 1; p.W = 1; p.Cin = K; p.Cout = O; p.k = 1; p.stride = 1; p.pad = 0; p.Ho = 1; p.Wo = 1;
+    int r = conv_fwd_tc(p, (cudaStream_t)stream);
+    MNB_REQUIRE(r != MNB_ERR_UNSUPPORTED, "fc_fwd_tc: %s", mnb_last_error());
+    return r;
+}
+
+int mnb_fc_dgrad_tc(const void* dyb, const float* w, const void* wpk, float* dx, int N, int K, int O, void* stream) {
+    MNB_REQUIRE(N > 0 && K % 8 == 0 && O % 8 == 0 && K > 0 && O > 0, "fc_dgrad_tc: K=%d, O=%d must be multiples of 8", K, O);
+    ConvP p = {};
+    p.dz = dyb; p.w = w; p.wpk = wpk; p.out = dx; p.out_f32 = 1;
+    p.N = N; p.H = 1; p.W = 1; p.Cin = K; p.Cout = O; p.k = 1; p.stride = 1; p.pad = 0; p.Ho = 1; p.Wo = 1;
+    int r = conv_dgrad_tc(p, (cudaStream_t)stream);
+    MNB_REQUIRE(r != MNB_ERR_UNSUPPORTED, "fc_dgrad_tc: %s", mnb_last_error());
+    return r;
+}
+
 int mnb_conv_wgrad(const void* x, const float* in_scale, const float* in_shift, const void* dz, float* dw, int N,
                    int H, int W, int Cin, int Cout, int k, int stride, int pad, int dtype, int x_layout, int impl,
                    void* stream) {

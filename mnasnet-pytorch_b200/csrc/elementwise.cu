@@ -454,6 +454,24 @@ struct AccumEpi {
     __device__ void operator()(int o, int k, float v) const { dw[(long long)o * ld + k] += v; }
 };
 
+__global__ void fc_prep_bf16_k(const float* __restrict__ x, const unsigned char* __restrict__ mask, float ms,
+                               bf16* __restrict__ xb, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = x[i];
+        if (mask) v = mask[i] ? v * ms : 0.f;
+        xb[i] = __float2bfloat16_rn(v);
+    }
+}
+__global__ void fc_gate_k(float* __restrict__ dx, const unsigned char* __restrict__ mask, float ms,
+                          const float* __restrict__ relu_ref, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = dx[i];
+        if (mask) v = mask[i] ? v * ms : 0.f;
+        if (relu_ref) v = relu_ref[i] > 0.f ? v : 0.f;
+        dx[i] = v;
+    }
+}
+
 __global__ void colsum_accum_k(const float* __restrict__ dy, float* db, int N, int O) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= O) return;
@@ -741,6 +759,28 @@ int mnb_fc_wgrad(const float* x, const unsigned char* mask, float mask_scale, co
         colsum_accum_k<<<(O + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dy, db, N, O);
         MNB_LAUNCH_CHECK("fc_wgrad(bias)");
     }
+    return 0;
+}
+
+int mnb_fc_prep_bf16(const float* x, const unsigned char* mask, float mask_scale, void* xb, long long n, void* stream) {
+    MNB_REQUIRE(n > 0, "fc_prep_bf16: empty");
+    fc_prep_bf16_k<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(x, mask, mask_scale, (bf16*)xb, n);
+    MNB_LAUNCH_CHECK("fc_prep_bf16");
+    return 0;
+}
+
+int mnb_fc_gate(float* dx, const unsigned char* mask, float mask_scale, const float* relu_ref, long long n,
+                void* stream) {
+    MNB_REQUIRE(n > 0, "fc_gate: empty");
+    fc_gate_k<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(dx, mask, mask_scale, relu_ref, n);
+    MNB_LAUNCH_CHECK("fc_gate");
+    return 0;
+}
+
+int mnb_fc_bias_grad(const float* dy, float* db, int N, int O, void* stream) {
+    MNB_REQUIRE(N > 0 && O > 0, "fc_bias_grad: bad shape");
+    colsum_accum_k<<<(O + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dy, db, N, O);
+    MNB_LAUNCH_CHECK("fc_bias_grad");
     return 0;
 }
 

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
     const int bres_bytes = (MODE != MODE_WGRAD && g.b_resident) ? BN * g.kpad * 2 : 0;
     unsigned char* sC = sBres + bres_bytes;                                   // epilogue stage
     const int c_pitch = BN * 2 + 16;
-    const int c_bytes = (MODE == MODE_WGRAD) ? 0 : 128 * c_pitch;
+    const int c_bytes = (MODE == MODE_WGRAD || p.out_f32) ? 0 : 128 * c_pitch;      // no staging for fp32-out GEMMs
     // dgrad with fused BN-backward reduction: per-group staging of the producer block's z tile (same geometry as sC)
     const int z_bytes = (MODE == MODE_DGRAD && p.bn_z != nullptr) ? c_bytes : 0;
     unsigned char* sZ = sC + 2 * c_bytes;
@@ -591,6 +591,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_k(ConvP p, TcGeom g) {
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[grp]);
+            } else if (p.out_f32) {
+                // classifier GEMMs: fp32 rows straight from the accumulator (no staging, no statistics)
+                const int ldo = (MODE == MODE_FWD) ? p.Cout : p.Cin;
+                float* orow = (float*)p.out + row_g * ldo + n0;
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(t_lane + c0, r);
+                    tmem_ld_wait();
+                    if (row_g < Mtot) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = n0 + c0 + j;
+                            if (col < Ntot) {
+                                float v = __uint_as_float(r[j]);
+                                if (MODE == MODE_FWD && p.bias) v += p.bias[col];
+                                if (p.relu_out) v = fmaxf(v, 0.f);
+                                orow[c0 + j] = v;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[grp]);
             } else {
                 const int ldo = (MODE == MODE_FWD) ? p.Cout : p.Cin;
                 for (int cb = 0; cb < BN; cb += 32) {          // batches of up to 32 columns: loads back to back, one wait
@@ -719,7 +742,8 @@ static bool tc_geom(int mode, const ConvP& p, TcGeom& g, size_t& smem, int& dept
         K = (long long)(p.ph_h ? 2 : 1) * (p.ph_w ? 2 : 1) * p.Cout;
         if (M <= 0) return false;
     }
-    if (p.nchw_in || p.Cin % 8 != 0 || p.Cout % 8 != 0) return false;
+    if (p.nchw_in || p.Cin % 8 != 0) return false;
+    if (p.Cout % 8 != 0 && !(mode == MODE_FWD && p.out_f32)) return false;
     const int nt = (Nn + 127) / 128;
     const int BN = ((Nn + nt - 1) / nt + 15) / 16 * 16;
     g.BN = BN;
@@ -734,7 +758,7 @@ static bool tc_geom(int mode, const ConvP& p, TcGeom& g, size_t& smem, int& dept
     g.stage_bytes = 128 * g.kc * 2 + ((mode == MODE_WGRAD || !g.b_resident) ? BN * g.kc * 2 : 0);
     const int xch = mode == MODE_DGRAD ? 0 : p.Cin;
     const size_t fixed = (g.b_resident ? (size_t)BN * g.kpad * 2 : 0) +
-                         (mode == MODE_WGRAD ? 0 : (size_t)2 * 128 * (BN * 2 + 16)) +
+                         ((mode == MODE_WGRAD || p.out_f32) ? 0 : (size_t)2 * 128 * (BN * 2 + 16)) +
                          ((mode == MODE_DGRAD && p.bn_z) ? (size_t)2 * 128 * (BN * 2 + 16) : 0) + (size_t)2 * xch * 4 + (128 + 512) * 4 +
                          (2 * MAXSTAGE + 4) * 8 + 16 + MAXSTAGE * 256 + 128;
     // deep ring of small stages when the chunk is small (memory-level parallelism), else 5 x up to 32 KB

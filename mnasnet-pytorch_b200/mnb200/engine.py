@@ -352,22 +352,38 @@ class Plan:
                 di += 1
             elif isinstance(ch, nn.Linear):
                 relu = i + 1 < len(children) and isinstance(children[i + 1], nn.ReLU)
-                y = self._f32(N, ch.out_features)
-                rec = {"x": cur, "mask": None, "ms": 1.0, "lin": ch, "y": y, "relu": relu, "K": width,
-                       "O": ch.out_features}
-                if pending is not None and pending[1] > 0:
+                O = ch.out_features
+                y = self._f32(N, O)
+                rec = {"x": cur, "mask": None, "ms": 1.0, "lin": ch, "y": y, "relu": relu, "K": width, "O": O,
+                       "tc": False}
+                drop = pending is not None and pending[1] > 0
+                if drop:
                     mask, p, idx = pending
                     rec.update(mask=mask, ms=1.0 / (1.0 - p), p=p, idx=idx)
                     self.fwd.append(_DropoutOp(self, mask, N * width, p, idx))
-                    self._op(self.fwd, "mnb_fc_fwd", cur, _MaskPtr(self, mask), _MaskScale(self, rec["ms"]),
-                             ch.weight, ch.bias, y, int(relu), N, width, ch.out_features)
+                maskp = _MaskPtr(self, rec["mask"]) if drop else None
+                msc = _MaskScale(self, rec["ms"]) if drop else 1.0
+                # bf16 mode: the classifier GEMMs run on the tensor pipe (tcgen05), fp32 accumulate and output
+                if self.eng.dtype == "bf16" and self.eng.impl != 1 and width % 8 == 0 and O % 8 == 0:
+                    xb = torch.empty((N, width), device=self.dev, dtype=torch.bfloat16)
+                    dyb = torch.empty((N, O), device=self.dev, dtype=torch.bfloat16)
+                    pf = torch.empty(O * width, device=self.dev, dtype=torch.bfloat16)
+                    pd = torch.empty(O * width, device=self.dev, dtype=torch.bfloat16)
+                    self.keep += [xb, dyb, pf, pd]
+                    rec.update(tc=True, xb=xb, dyb=dyb, pf=pf, pd=pd)
+                    for ops, train in ((self.fwd, True), (self.fwd_eval, False)):
+                        self._op(ops, "mnb_pack_weights", ch.weight, pf, pd if train else None, O, width, 1,
+                                 label="pack_weights")
+                        self._op(ops, "mnb_fc_prep_bf16", cur, maskp if train else None, msc if train else 1.0, xb,
+                                 N * width)
+                        self._op(ops, "mnb_fc_fwd_tc", xb, ch.weight, pf, ch.bias, y, int(relu), N, width, O,
+                                 label="fc_fwd(tcgen05)")
                 else:
-                    self._op(self.fwd, "mnb_fc_fwd", cur, None, 1.0, ch.weight, ch.bias, y, int(relu), N, width,
-                             ch.out_features)
-                self._op(self.fwd_eval, "mnb_fc_fwd", cur, None, 1.0, ch.weight, ch.bias, y, int(relu), N,
-                         width, ch.out_features)
+                    self._op(self.fwd, "mnb_fc_fwd", cur, maskp, msc, ch.weight, ch.bias, y, int(relu), N, width, O)
+                    self._op(self.fwd_eval, "mnb_fc_fwd", cur, None, 1.0, ch.weight, ch.bias, y, int(relu), N,
+                             width, O)
                 self.head.append(rec)
-                cur, width, pending = y, ch.out_features, None
+                cur, width, pending = y, O, None
             elif isinstance(ch, nn.ReLU):
                 pass
             else:
@@ -408,11 +424,20 @@ class Plan:
                 lin = r["lin"]
                 maskp = _MaskPtr(self, r["mask"]) if r["mask"] is not None else None
                 ms = _MaskScale(self, r["ms"]) if r["mask"] is not None else 1.0
-                self._op(ops, "mnb_fc_wgrad", r["x"], maskp, ms, g, _G(lin.weight), _G(lin.bias), self.N, r["K"],
-                         r["O"])
                 dx = self._f32(self.N, r["K"])
                 relu_ref = r["x"] if (i > 0 and self.head[i - 1]["relu"]) else None
-                self._op(ops, "mnb_fc_dgrad", g, lin.weight, maskp, ms, relu_ref, dx, self.N, r["K"], r["O"])
+                if r["tc"]:
+                    self._op(ops, "mnb_fc_prep_bf16", g, None, 1.0, r["dyb"], self.N * r["O"])
+                    self._op(ops, "mnb_conv_wgrad", r["xb"], None, None, r["dyb"], _G(lin.weight), self.N, 1, 1,
+                             r["K"], r["O"], 1, 1, 0, _lib.MNB_BF16, _lib.LAYOUT_NHWC, 0, label="fc_wgrad(tcgen05)")
+                    self._op(ops, "mnb_fc_bias_grad", g, _G(lin.bias), self.N, r["O"])
+                    self._op(ops, "mnb_fc_dgrad_tc", r["dyb"], lin.weight, r["pd"], dx, self.N, r["K"], r["O"],
+                             label="fc_dgrad(tcgen05)")
+                    self._op(ops, "mnb_fc_gate", dx, maskp, ms, relu_ref, self.N * r["K"])
+                else:
+                    self._op(ops, "mnb_fc_wgrad", r["x"], maskp, ms, g, _G(lin.weight), _G(lin.bias), self.N,
+                             r["K"], r["O"])
+                    self._op(ops, "mnb_fc_dgrad", g, lin.weight, maskp, ms, relu_ref, dx, self.N, r["K"], r["O"])
                 g = dx
             gbuf = take()
             hi = self.head_in

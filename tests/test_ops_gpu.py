@@ -441,3 +441,48 @@ def test_argument_errors_are_reported():
     assert rc == -1
     with pytest.raises(L.MnbError):
         L.call("mnb_bn_relu_apply", P(x), P(x), P(x), None, P(x), 4, 12, 0, stream())
+
+
+@pytest.mark.parametrize("N,K,O,relu", [(37, 320, 512, 1), (256, 512, 1000, 0), (5, 320, 1003, 0)])
+def test_fc_on_tcgen05(N, K, O, relu):
+    """Classifier GEMMs on the tensor pipe (bf16 operands, fp32 accumulate/output) vs fp64."""
+    L = _lib()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(N, K, generator=g)
+    w = torch.randn(O, K, generator=g) / math.sqrt(K)
+    b = torch.randn(O, generator=g) * 0.1
+    mask = (torch.rand(N, K, generator=g) > 0.5).to(torch.uint8)
+    xd, wd, bd, md = x.cuda(), w.cuda(), b.cuda(), mask.cuda()
+    xb = torch.empty(N, K, device="cuda", dtype=torch.bfloat16)
+    pf = torch.empty(O * K, device="cuda", dtype=torch.bfloat16)
+    pd = torch.empty(O * K, device="cuda", dtype=torch.bfloat16)
+    L.call("mnb_pack_weights", P(wd), P(pf), P(pd), O, K, 1, stream())
+    L.call("mnb_fc_prep_bf16", P(xd), P(md), 2.0, P(xb), N * K, stream())
+    y = torch.empty(N, O, device="cuda")
+    L.call("mnb_fc_fwd_tc", P(xb), P(wd), P(pf), P(bd), P(y), relu, N, K, O, stream())
+    torch.cuda.synchronize()
+    xm = xb.float().cpu().double()
+    assert rel(xm, x.double() * mask.double() * 2.0) < 5e-3
+    ref = xm @ w.to(torch.bfloat16).double().t() + b.double()
+    ref = torch.relu(ref) if relu else ref
+    assert rel(y, ref) < 1e-4                     # same bf16 operands, fp32 accumulate
+    if O % 8 == 0:
+        dy = torch.randn(N, O, generator=g)
+        dyb = torch.empty(N, O, device="cuda", dtype=torch.bfloat16)
+        L.call("mnb_fc_prep_bf16", P(dy.cuda()), None, 1.0, P(dyb), N * O, stream())
+        dx = torch.empty(N, K, device="cuda")
+        L.call("mnb_fc_dgrad_tc", P(dyb), P(wd), P(pd), P(dx), N, K, O, stream())
+        ref_dx = dyb.float().cpu().double() @ w.to(torch.bfloat16).double()
+        torch.cuda.synchronize()
+        assert rel(dx, ref_dx) < 1e-4
+        rr = torch.randn(N, K, generator=g)
+        L.call("mnb_fc_gate", P(dx), P(md), 2.0, P(rr.cuda()), N * K, stream())
+        torch.cuda.synchronize()
+        assert rel(dx, ref_dx * mask.double() * 2.0 * (rr.double() > 0)) < 1e-4
+        dw = torch.zeros(O, K, device="cuda")
+        L.call("mnb_conv_wgrad", P(xb), None, None, P(dyb), P(dw), N, 1, 1, K, O, 1, 1, 0, 1, 0, 0, stream())
+        db = torch.zeros(O, device="cuda")
+        L.call("mnb_fc_bias_grad", P(dy.cuda()), P(db), N, O, stream())
+        torch.cuda.synchronize()
+        assert rel(dw, dyb.float().cpu().double().t() @ xm) < 1e-4
+        assert rel(db, dy.double().sum(0)) < 1e-5
