@@ -70,10 +70,13 @@ def test_fp32_step_matches_oracle(n, h, w, tag):
     err = rel(gcat(names, ours), gcat(names, g64))
     print(f"[{tag}] logits rel {rel(out, logits32):.2e}  grad ours-vs-fp64 {err:.2e}  oracle fp32-vs-fp64 {floor:.2e}")
     assert err < 2 * floor + 1e-4
-    # head gradients are far from the ReLU-flip noise: tight
+    # the last linear layer is far from the ReLU-flip noise: tight.  Layers behind the hidden ReLU can see a mask
+    # flip between fp32 and fp64 (F9): same bound as the rest of the network
     for k in names:
-        if k.startswith("classifier"):
+        if k.startswith("classifier.4"):
             assert rel(ours[k], g64[k]) < 1e-4, k
+        elif k.startswith("classifier"):
+            assert rel(ours[k], g64[k]) < 2 * floor + 1e-3, k
     # conv-bias gradients are analytically zero
     for k in names:
         if k.endswith("conv.bias"):
@@ -186,9 +189,11 @@ def test_other_heads_and_dropout(cfg, nc):
     loss.backward()
     sd, tr, logits, oloss, g = oracle_run(2, 64, 64, cfg, nc)
     assert rel(out, logits) < 1e-4
+    last = max(int(k.split(".")[1]) for k, _ in m.named_parameters() if k.startswith("classifier"))
     for k, p in m.named_parameters():
         if k.startswith("classifier"):
-            assert rel(p.grad, g[k]) < 1e-3, k
+            # tight on the last linear layer; behind a hidden ReLU a single fp32 mask flip moves a row (F9)
+            assert rel(p.grad, g[k]) < (1e-3 if int(k.split(".")[1]) == last else 2e-2), k
     # dropout active: masks are drawn on the device; injected masks reproduce the oracle exactly
     for mod in m.modules():
         if isinstance(mod, torch.nn.Dropout):
@@ -267,7 +272,7 @@ def test_shape_polymorphism(n, h, w, dtype):
         assert torch.equal(out.argmax(1).cpu(), logits32.argmax(1))
         for k, p in m.named_parameters():
             if k.startswith("classifier"):
-                assert rel(p.grad, g32[k]) < 1e-3, k
+                assert rel(p.grad, g32[k]) < (1e-3 if k.startswith("classifier.4") else 2e-2), k
     else:
         assert torch.isfinite(out).all()
         assert all(torch.isfinite(p.grad).all() for p in m.parameters())
