@@ -36,4 +36,9 @@ int conv_fwd_tc(const ConvP& p, cudaStream_t st);
 int conv_dgrad_tc(const ConvP& p, cudaStream_t st);
 int conv_wgrad_tc(const ConvP& p, cudaStream_t st);
 
+// warp-streaming mma.sync path for the small-channel 1x1 layers (pw_stream.cu); MNB_ERR_UNSUPPORTED otherwise
+int conv_fwd_stream(const ConvP& p, cudaStream_t st);
+int conv_dgrad_stream(const ConvP& p, cudaStream_t st);
+int conv_wgrad_stream(const ConvP& p, cudaStream_t st);
+
 }  // namespace mnb

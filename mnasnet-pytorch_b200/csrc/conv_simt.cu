@@ -10,6 +10,8 @@
 //   DGRAD C[m=(n,h,w)][ci]        = sum_kk dz(m,kk) w(ci,kk)       kk=(kh,kw,co)  A chunk: 8 co  (vector load)
 //   WGRAD C[co][kk=(kh,kw,ci)]    = sum_pos dz(pos,co) a(pos,kk)   K = positions  chunks run along M / N
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "conv_params.cuh"
 
 namespace mnb {
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(256) conv_simt_k(ConvP p) {
 bool stem_supported(int Cin, int Cout, int k, int stride, int pad, int nchw_in);
 int stem_fwd(const float* x, const float* w, const float* bias, void* z, double* stats, int N, int H, int W, int dtype,
              cudaStream_t st);
-int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, int dtype, cudaStream_t st);
+int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, int dtype, int impl, cudaStream_t st);
 
 __global__ void pack_weights_k(const float* __restrict__ w, bf16* __restrict__ pf, bf16* __restrict__ pd, int Cout,
                                int Cin, int kk2) {
@@ -341,6 +343,17 @@ int conv_wgrad_simt(ConvP p, int dtype, cudaStream_t st) {
 
 using namespace mnb;
 
+// impl 3 prefers the warp-streaming path of pw_stream.cu where it is instantiated; impl 0 (auto) does the same when
+// MNB_PW_STREAM=1 is set in the environment (read once).  Shapes it does not cover continue to tcgen05 / SIMT.
+static bool prefer_stream(int impl) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("MNB_PW_STREAM");
+        env = (e && e[0] == '1') ? 1 : 0;
+    }
+    return impl == 3 || (impl == 0 && env == 1);
+}
+
 extern "C" {
 
 int mnb_pack_weights(const float* w, void* wpk_fwd, void* wpk_dgrad, int Cout, int Cin, int k, void* stream) {
@@ -379,6 +392,10 @@ int mnb_conv_fwd_packed(const void* x, const float* in_scale, const float* in_sh
     p.nchw_in = x_layout == MNB_LAYOUT_NCHW_F32;
     if (impl != 1 && in_scale == nullptr && stem_supported(Cin, Cout, k, stride, pad, p.nchw_in))
         return stem_fwd((const float*)x, w, bias, z, stats, N, H, W, dtype, (cudaStream_t)stream);
+    if (dtype == MNB_BF16 && prefer_stream(impl)) {
+        int r = conv_fwd_stream(p, (cudaStream_t)stream);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (impl != 1 && dtype == MNB_BF16) {
         int r = conv_fwd_tc(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -398,6 +415,10 @@ int mnb_conv_dgrad_packed(const void* dz, const float* w, const void* wpk, const
     p.bn_z = bn_z; p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.stats = bn_z ? bn_sums : nullptr;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
+    if (dtype == MNB_BF16 && prefer_stream(impl)) {
+        int r = conv_dgrad_stream(p, (cudaStream_t)stream);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (impl != 1 && dtype == MNB_BF16) {
         int r = conv_dgrad_tc(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -437,7 +458,11 @@ int mnb_conv_wgrad(const void* x, const float* in_scale, const float* in_shift, 
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
     p.nchw_in = x_layout == MNB_LAYOUT_NCHW_F32;
     if (impl != 1 && in_scale == nullptr && stem_supported(Cin, Cout, k, stride, pad, p.nchw_in))
-        return stem_wgrad((const float*)x, dz, dw, N, H, W, dtype, (cudaStream_t)stream);
+        return stem_wgrad((const float*)x, dz, dw, N, H, W, dtype, impl, (cudaStream_t)stream);
+    if (dtype == MNB_BF16 && prefer_stream(impl)) {
+        int r = conv_wgrad_stream(p, (cudaStream_t)stream);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (impl != 1 && dtype == MNB_BF16) {
         int r = conv_wgrad_tc(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;

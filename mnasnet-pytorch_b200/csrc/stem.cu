@@ -9,6 +9,8 @@
 //            persistent pixel loop, one smem + fp64-atomic flush per CTA.
 //   wgrad  : thread == (pixel slot, 4-channel group): 27 taps x 4 channels of partial sums in registers over a
 //            persistent pixel loop; smem + fp32-atomic flush per CTA.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mnb {
@@ -137,6 +139,142 @@ __global__ void __launch_bounds__(256) stem_wgrad_k(const float* __restrict__ x,
     for (int i = threadIdx.x; i < COUT * STEM_TAPS; i += blockDim.x) atomicAdd(&dw[i], sred[i]);
 }
 
+// ---- backward-weight on the tensor pipe (bf16 activations) ---------------------------------------------------------
+// dw[co][tap] = sum_pix dz[pix][co] * patch[pix][tap] as an implicit GEMM with M = 32 output channels, N = 27 (-> 32)
+// taps and the output pixels as the reduction index.  A warp takes 16 consecutive output pixels per step: it stages
+// their dz rows and their bf16-rounded input patches in a private shared buffer (the next step's global loads are
+// already in flight), reads both back transposed with ldmatrix.trans and issues 2 x 4 mma.sync.m16n8k16.  No
+// cross-warp synchronisation until the final reduction; replaces 108 fp32 accumulators per lane (254 registers, 8
+// warps per SM, latency-bound at 0.3 TB/s) of stem_wgrad_k.
+__device__ __forceinline__ void stem_mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void stem_ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+
+__global__ void __launch_bounds__(128, 4) stem_wgrad_mma_k(const float* __restrict__ x, const bf16* __restrict__ dz,
+                                                           float* dw, int N, int H, int W, int Ho, int Wo) {
+    constexpr int WARPS = 4, PITCH = 80;                 // 64 bytes of payload per staged row, pitch = 5 x 16 bytes
+    constexpr int SEGS = 5;                              // (ci,kh) segments of 3 taps per lane: lanes 0-15 take 0-4, 16-31 take 5-8
+    __shared__ __align__(16) unsigned char s_z[WARPS][16 * PITCH];
+    __shared__ __align__(16) unsigned char s_p[WARPS][16 * PITCH];
+    __shared__ float s_dw[32 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_dw[i] = 0.f;
+    for (int i = threadIdx.x; i < WARPS * 16 * PITCH / 4; i += blockDim.x) {
+        reinterpret_cast<uint32_t*>(&s_z[0][0])[i] = 0u;
+        reinterpret_cast<uint32_t*>(&s_p[0][0])[i] = 0u;  // taps 27..31 stay zero for the whole kernel
+    }
+    __syncthreads();
+
+    const int HWo = Ho * Wo;
+    const int total = N * HWo;                           // host guarantees < 2^31
+    const int nsteps = (total + 15) / 16;
+    const int wstride = gridDim.x * WARPS;
+    int step = blockIdx.x * WARPS + warp;
+    const int pix = lane & 15, half = lane >> 4;
+
+    float xr[SEGS][3];
+    uint4 zr[2];
+    auto load_step = [&](int st) {
+        const int p0 = st * 16;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c = lane + 32 * i, r = c >> 2, cc = c & 3;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (p0 + r < total) v = __ldg(reinterpret_cast<const uint4*>(dz + (long long)(p0 + r) * 32 + cc * 8));
+            zr[i] = v;
+        }
+        const int p = p0 + pix;
+        const bool pok = p < total;
+        const int n = p / HWo, rem = p - n * HWo, ho = rem / Wo, wo = rem - ho * Wo;
+        const int iw0 = 2 * wo - 1;
+#pragma unroll
+        for (int i = 0; i < SEGS; ++i) {
+            const int seg = half * SEGS + i;             // (ci,kh) = (seg / 3, seg % 3); seg 9 does not exist
+            const int ci = seg / 3, kh = seg - 3 * ci;
+            const int ih = 2 * ho - 1 + kh;
+            const bool rok = pok && seg < 9 && ih >= 0 && ih < H;
+            const float* xp = x + (((long long)n * STEM_CIN + ci) * H + ih) * W + iw0;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iw = iw0 + kw;
+                xr[i][kw] = (rok && iw >= 0 && iw < W) ? __ldg(xp + kw) : 0.f;
+            }
+        }
+    };
+    if (step < nsteps) load_step(step);
+
+    unsigned char* wz = s_z[warp];
+    unsigned char* wp = s_p[warp];
+    const int lm = lane >> 3, lr = lane & 7;
+    const unsigned char* a_addr = wz + (lr + ((lm & 2) ? 8 : 0)) * PITCH + ((lm & 1) ? 16 : 0);   // + 32*m
+    const unsigned char* b_addr = wp + (lr + ((lm & 1) ? 8 : 0)) * PITCH + ((lm & 2) ? 16 : 0);   // + 32*(n/2)
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+
+    for (; step < nsteps; step += wstride) {
+        __syncwarp();                                    // the previous step's ldmatrix reads are done
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c = lane + 32 * i, r = c >> 2, cc = c & 3;
+            *reinterpret_cast<uint4*>(wz + r * PITCH + cc * 16) = zr[i];
+        }
+#pragma unroll
+        for (int i = 0; i < SEGS; ++i) {
+            const int seg = half * SEGS + i;
+            if (seg < 9) {
+                bf16* pp = reinterpret_cast<bf16*>(wp + pix * PITCH) + 3 * seg;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) pp[kw] = __float2bfloat16_rn(xr[i][kw]);
+            }
+        }
+        __syncwarp();
+        if (step + wstride < nsteps) load_step(step + wstride);
+        uint32_t b[4][2];
+#pragma unroll
+        for (int n = 0; n < 4; n += 2) {
+            uint32_t r4[4];
+            stem_ldmatrix_x4_trans(r4, b_addr + 16 * n);
+            b[n][0] = r4[0]; b[n][1] = r4[1]; b[n + 1][0] = r4[2]; b[n + 1][1] = r4[3];
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            uint32_t a[4];
+            stem_ldmatrix_x4_trans(a, a_addr + 32 * m);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) stem_mma16816(acc[m][n], a, b[n][0], b[n][1]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const int co = 16 * m + g, tap = 8 * n + 2 * t;
+            atomicAdd(&s_dw[co * 32 + tap], acc[m][n][0]);
+            atomicAdd(&s_dw[co * 32 + tap + 1], acc[m][n][1]);
+            atomicAdd(&s_dw[(co + 8) * 32 + tap], acc[m][n][2]);
+            atomicAdd(&s_dw[(co + 8) * 32 + tap + 1], acc[m][n][3]);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * STEM_TAPS; i += blockDim.x) {
+        const int co = i / STEM_TAPS, tap = i - co * STEM_TAPS;
+        atomicAdd(&dw[i], s_dw[co * 32 + tap]);
+    }
+}
+
 bool stem_supported(int Cin, int Cout, int k, int stride, int pad, int nchw_in) {
     return nchw_in && Cin == 3 && Cout == 32 && k == 3 && stride == 2 && pad == 1;
 }
@@ -154,12 +292,22 @@ int stem_fwd(const float* x, const float* w, const float* bias, void* z, double*
     return 0;
 }
 
-int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, int dtype, cudaStream_t st) {
+int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, int dtype, int impl, cudaStream_t st) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)N * Ho * Wo;
     long long blocks = cdiv(total, 32);
     const long long cap = (long long)num_sms() * 4;
     if (blocks > cap) blocks = cap;
+    static int use_mma = -1;                             // MNB_STEM_MMA=1: tensor-pipe variant for bf16 (read once)
+    if (use_mma < 0) {
+        const char* e = getenv("MNB_STEM_MMA");
+        use_mma = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (dtype == MNB_BF16 && (use_mma || impl == 3) && total < (1ll << 31) - 64) {
+        stem_wgrad_mma_k<<<num_sms() * 4, 128, 0, st>>>(x, (const bf16*)dz, dw, N, H, W, Ho, Wo);
+        MNB_LAUNCH_CHECK("stem_wgrad(mma)");
+        return 0;
+    }
     if (dtype == MNB_F32) stem_wgrad_k<float, 32><<<(unsigned)blocks, 256, 0, st>>>(x, (const float*)dz, dw, N, H, W, Ho, Wo);
     else stem_wgrad_k<bf16, 32><<<(unsigned)blocks, 256, 0, st>>>(x, (const bf16*)dz, dw, N, H, W, Ho, Wo);
     MNB_LAUNCH_CHECK("stem_wgrad");

@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import lib, check
 
 DTYPES = {"fp32": (_lib.MNB_F32, torch.float32), "bf16": (_lib.MNB_BF16, torch.bfloat16)}
-IMPLS = {"auto": 0, "simt": 1, "tc": 2}
+IMPLS = {"auto": 0, "simt": 1, "tc": 2, "stream": 3}
 BN_EPS_DEFAULT = 1e-5
 
 
