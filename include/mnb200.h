@@ -46,9 +46,10 @@ int mnb_device_is_sm100(void);
 /* ---- dense convolution (groups=1; k in {1,3}; stride in {1,2}) : nn.Conv2d, mnasnet.py:48-54 -------------
  * z[n,ho,wo,co] = bias[co] + sum_{kh,kw,ci} a(n, ho*stride-pad+kh, wo*stride-pad+kw, ci) * w[co,ci,kh,kw]
  * w is the torch layout [Cout,Cin,k,k] fp32.  x_layout selects NHWC(dtype) or NCHW fp32 (stem only).
- * impl: 0 = auto (tcgen05 for bf16 where available), 1 = force SIMT, 2 = force tcgen05, 3 = prefer the
- * warp-streaming mma.sync kernels for the small-channel 1x1 layers (needs the packed weight for fwd/dgrad; shapes it
- * does not cover fall through to tcgen05 / SIMT).  MNB_PW_STREAM=1 in the environment makes 0 behave like 3. */
+ * impl: 0 = auto: bf16 1x1 layers with Cin, Cout <= 72 and a packed weight take the warp-streaming mma.sync kernels
+ *           (pw_stream.cu; backward-weight needs no packing), everything else bf16 takes tcgen05, fp32 takes SIMT;
+ *       1 = force SIMT, 2 = force tcgen05 (bf16), 3 = like auto regardless of MNB_PW_STREAM / MNB_STEM_MMA.
+ * MNB_PW_STREAM=0 / MNB_STEM_MMA=0 in the environment keep auto on the tcgen05 / fp32-input stem kernels. */
 int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                  void* z, double* stats, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                  int dtype, int x_layout, int impl, void* stream);

@@ -298,12 +298,14 @@ int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, i
     long long blocks = cdiv(total, 32);
     const long long cap = (long long)num_sms() * 4;
     if (blocks > cap) blocks = cap;
-    static int use_mma = -1;                             // MNB_STEM_MMA=1: tensor-pipe variant for bf16 (read once)
+    // bf16: tensor-pipe kernel (11x faster, profiles/r1_exp_stream.json) unless impl 2 asks for the fp32-input SIMT
+    // kernel or MNB_STEM_MMA=0 is set (read once)
+    static int use_mma = -1;
     if (use_mma < 0) {
         const char* e = getenv("MNB_STEM_MMA");
-        use_mma = (e && e[0] == '1') ? 1 : 0;
+        use_mma = (e && e[0] == '0') ? 0 : 1;
     }
-    if (dtype == MNB_BF16 && (use_mma || impl == 3) && total < (1ll << 31) - 64) {
+    if (dtype == MNB_BF16 && (impl == 3 || (impl == 0 && use_mma)) && total < (1ll << 31) - 64) {
         stem_wgrad_mma_k<<<num_sms() * 4, 128, 0, st>>>(x, (const bf16*)dz, dw, N, H, W, Ho, Wo);
         MNB_LAUNCH_CHECK("stem_wgrad(mma)");
         return 0;
