@@ -825,6 +825,16 @@ class Engine:
         """Same as train_step, replayed from a CUDA graph captured per input shape.  x / target are copied
         into static buffers; lr and the step counter are read from device scalars so the schedule can change
         between replays (train.py:282-302,334)."""
+        graph, sx, st, plan = self.capture_step_graph(x, target, lr, betas, eps)
+        sx.copy_(x, non_blocking=True)
+        st.copy_(target, non_blocking=True)
+        self.dev_lr.fill_(float(lr))
+        graph.replay()
+        return plan.loss
+
+    def capture_step_graph(self, x, target, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        """Captures (once per input shape) the CUDA graph of the fused step without advancing the training state:
+        the eager warm-up step it needs is rolled back (parameters, BN buffers, optimizer moments, counters)."""
         if self.grad_hook is not None:
             raise RuntimeError("graph replay is single-GPU; use train_step with GradSync for data parallel")
         self._check_store()
@@ -843,26 +853,21 @@ class Engine:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             saved = (self.store.flat.clone(), self.store.fbuf.clone(), self.store.ibuf.clone(),
-                     self.dev_step.clone(), self.host_step)
+                     self.dev_step.clone(), self.host_step, self.store.m.clone(), self.store.v.clone())
             with torch.cuda.stream(s):
                 self._graph_body(sx, st, betas, eps)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.store.flat.copy_(saved[0]); self.store.fbuf.copy_(saved[1]); self.store.ibuf.copy_(saved[2])
             self.dev_step.copy_(saved[3]); self.host_step = saved[4]
-            self.store.m.zero_(); self.store.v.zero_()
+            self.store.m.copy_(saved[5]); self.store.v.copy_(saved[6])     # (a resumed optimizer state survives)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._graph_body(sx, st, betas, eps)
             # capture does not execute: state is untouched
             g = (graph, sx, st, plan)
             self.graphs[key] = g
-        graph, sx, st, plan = g
-        sx.copy_(x, non_blocking=True)
-        st.copy_(target, non_blocking=True)
-        self.dev_lr.fill_(float(lr))
-        graph.replay()
-        return plan.loss
+        return g
 
     def _graph_body(self, sx, st, betas, eps):
         plan = self.forward(sx, True)

@@ -1,0 +1,165 @@
+"""GPU: the warp-streaming 1x1 kernels and the tensor-pipe stem backward-weight (csrc/pw_stream.cu, csrc/stem.cu)
+against the tcgen05 / SIMT kernels of the same C-ABI entry points and against torch fp32 math; checkpoint resume and
+validation through the engine.  Runs last (file name) so that a problem here cannot hide the core parity suite."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_ops_gpu import P, STREAM_SHAPES, _lib, rel, stream
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("xform", [True, False])
+@pytest.mark.parametrize("rows", [(1, 5, 7), (2, 16, 16), (3, 28, 28)])
+@pytest.mark.parametrize("chans", sorted(STREAM_SHAPES))
+def test_pw_stream_matches_tcgen05(chans, rows, xform):
+    """Warp-streaming 1x1 kernels (impl 3) vs the tcgen05 kernels (impl 2) on the same bf16 operands: forward + BN
+    statistics, backward-data with and without the residual, backward-weight; and vs torch fp32 math."""
+    L = _lib()
+    Cin, Cout = chans
+    N, H, W = rows
+    M = N * H * W
+    bf = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(M + 7 * Cin + Cout)
+    x = torch.randn(M, Cin, device="cuda", generator=g).to(bf)
+    w = (torch.randn(Cout, Cin, 1, 1, device="cuda", generator=g) / math.sqrt(Cin)).float()
+    b = (torch.randn(Cout, device="cuda", generator=g) * 0.1).float()
+    sc = (torch.rand(Cin, device="cuda", generator=g) + 0.5).float() if xform else None
+    sh = (torch.randn(Cin, device="cuda", generator=g) * 0.3).float() if xform else None
+    dz = torch.randn(M, Cout, device="cuda", generator=g).to(bf)
+    add = torch.randn(M, Cin, device="cuda", generator=g).to(bf)
+    pf = torch.empty(Cout * Cin, device="cuda", dtype=bf)
+    pd = torch.empty(Cout * Cin, device="cuda", dtype=bf)
+    L.call("mnb_pack_weights", P(w), P(pf), P(pd), Cout, Cin, 1, stream())
+
+    def close(a, ref):
+        a, ref = a.float(), ref.float()
+        tol = torch.maximum(a.abs(), ref.abs()) * 2.0 ** -6 + 1e-4 * ref.abs().mean()
+        return bool(((a - ref).abs() <= tol).all()) and rel(a, ref) < 2e-3
+
+    res = {}
+    for impl in (2, 3):
+        z = torch.full((M, Cout), float("nan"), device="cuda", dtype=bf)
+        st = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
+        L.call("mnb_conv_fwd_packed", P(x), P(sc), P(sh), P(w), P(pf), P(b), P(z), P(st), N, H, W, Cin, Cout, 1, 1, 0,
+               1, 0, impl, stream())
+        dx = torch.full((M, Cin), float("nan"), device="cuda", dtype=bf)
+        L.call("mnb_conv_dgrad_packed", P(dz), P(w), P(pd), P(add), P(dx), None, None, None, None, N, H, W, Cin, Cout,
+               1, 1, 0, 1, impl, stream())
+        dx0 = torch.full((M, Cin), float("nan"), device="cuda", dtype=bf)
+        L.call("mnb_conv_dgrad_packed", P(dz), P(w), P(pd), None, P(dx0), None, None, None, None, N, H, W, Cin, Cout,
+               1, 1, 0, 1, impl, stream())
+        dw = torch.zeros(Cout, Cin, device="cuda", dtype=torch.float32)
+        for _ in range(2):                                  # accumulates INTO dw
+            L.call("mnb_conv_wgrad", P(x), P(sc), P(sh), P(dz), P(dw), N, H, W, Cin, Cout, 1, 1, 0, 1, 0, impl,
+                   stream())
+        torch.cuda.synchronize()
+        res[impl] = (z, st, dx, dx0, dw)
+    z3, st3, dx3, dx03, dw3 = res[3]
+    z2, st2, dx2, dx02, dw2 = res[2]
+    assert torch.isfinite(z3.float()).all() and torch.isfinite(dx3.float()).all() and torch.isfinite(dx03.float()).all()
+    assert close(z3, z2) and close(dx3, dx2) and close(dx03, dx02)
+    assert rel(st3, st2) < 1e-4
+    assert rel(dw3, dw2) < 1e-4
+    a = x.float()
+    if xform:
+        a = torch.relu(a * sc + sh).to(bf).float()
+    assert rel(z3.float(), a @ w.view(Cout, Cin).to(bf).float().t() + b) < 5e-3      # bf16 output rounding
+    assert rel(dw3, 2 * (dz.float().t() @ a)) < 1e-4
+    zs = z3.double()
+    torch.testing.assert_close(st3[:Cout], zs.sum(0), rtol=1e-5, atol=1e-5 * M ** 0.5)
+    torch.testing.assert_close(st3[Cout:], (zs * zs).sum(0), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 30, 26), (3, 64, 64), (1, 17, 23)])
+def test_stem_wgrad_tensor_pipe_matches_simt(shape):
+    """bf16 stem backward-weight: mma.sync kernel (auto / impl 3; input rounded to bf16) vs the fp32-input kernel."""
+    L = _lib()
+    N, H, W = shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    g = torch.Generator(device="cuda").manual_seed(N + H)
+    x = torch.randn(N, 3, H, W, device="cuda", generator=g)
+    dz = torch.randn(N, Ho, Wo, 32, device="cuda", generator=g).to(torch.bfloat16)
+    dws = {}
+    for impl in (2, 3, 0):
+        dw = torch.zeros(32, 3, 3, 3, device="cuda")
+        L.call("mnb_conv_wgrad", P(x), None, None, P(dz), P(dw), N, H, W, 3, 32, 3, 2, 1, 1, 1, impl, stream())
+        torch.cuda.synchronize()
+        dws[impl] = dw
+    assert rel(dws[3], dws[2]) < 5e-3
+    assert rel(dws[0], dws[2]) < 5e-3
+    xr = x.double().cpu().requires_grad_(False)
+    w_ = torch.zeros(32, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xr, w_, None, stride=2, padding=1).backward(dz.double().cpu().permute(0, 3, 1, 2).contiguous())
+    assert rel(dws[3], w_.grad) < 5e-3
+
+
+def _build(dtype, seed=42):
+    from test_net_gpu import build
+    return build(dtype, seed=seed)
+
+
+def test_validate_matches_eval_forward_and_oracle():
+    """validate() = eval forward + CrossEntropyLoss + precision@1/@5, weighted by batch size."""
+    from mnb200 import engine, evaluate
+    from oracle import mnasnet_oracle as O
+    m = _build("fp32")
+    eng = engine.engine_for(m)
+    batches = [O.synthetic_batch(3, 96, 128), O.synthetic_batch(5, 64, 64)]
+    m(batches[0][0].cuda())                                  # one train forward moves the running statistics
+    m.eval()
+    res = evaluate.validate(eng, batches, topk=(1, 5))
+    tot, loss, a1, a5 = 0, 0.0, 0.0, 0.0
+    with torch.no_grad():
+        for x, t in batches:
+            out = m(x.cuda())
+            n = t.shape[0]
+            loss += F.cross_entropy(out, t.cuda()).item() * n
+            rank = (out > out.gather(1, t.cuda()[:, None])).sum(1)
+            a1 += 100.0 * (rank < 1).float().mean().item() * n
+            a5 += 100.0 * (rank < 5).float().mean().item() * n
+            tot += n
+    assert res["n"] == tot == 8
+    assert abs(res["loss"] - loss / tot) < 1e-5 * max(1.0, loss / tot)
+    assert abs(res["acc1"] - a1 / tot) < 1e-3 and abs(res["acc5"] - a5 / tot) < 1e-3
+    # and the eval logits are the oracle's eval logits
+    torch.manual_seed(42)
+    sd = O.init_state_dict()
+    with torch.no_grad():
+        O.forward(sd, batches[0][0], True, dropout_masks="off")
+        ref = O.forward(sd, batches[1][0], False)
+    got = evaluate.eval_logits(eng, batches[1][0].cuda())
+    assert rel(got, ref) < 1e-4
+
+
+def test_resume_restores_model_and_optimizer_state():
+    """a checkpoint in the reference's format, written after two fused steps, resumes into a fresh
+    model + engine (parameters, BN buffers, Adam moments, step counter): the third step is identical."""
+    from mnb200 import checkpoint, engine
+    from oracle import mnasnet_oracle as O
+    x, t = O.synthetic_batch(4, 64, 64)
+    xd, td = x.cuda(), t.cuda()
+    m = _build("fp32")
+    eng = engine.engine_for(m)
+    for _ in range(2):
+        eng.train_step(xd, td, lr=1e-3)
+    state = checkpoint.make_checkpoint(m, eng, epoch=3, best_loss=1.5)
+    assert len(state["state_dict"]) == 403 and len(state["optimizer"]["state"]) == 112
+    l3 = eng.train_step(xd, td, lr=1e-3).item()
+    m2 = _build("fp32", seed=7)
+    eng2 = engine.engine_for(m2)
+    epoch, best = checkpoint.resume(state, m2, eng2, load_optimizer=True)
+    assert (epoch, best) == (3, 1.5) and eng2.host_step == 2
+    l3b = eng2.train_step(xd, td, lr=1e-3).item()
+    assert abs(l3 - l3b) <= 1e-5 * abs(l3)
+    torch.cuda.synchronize()
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        if k.endswith("conv.bias"):
+            continue        # analytically zero gradient: Adam normalises rounding noise into a random walk (F9)
+        if a.dtype.is_floating_point:
+            assert rel(b, a) < 1e-4, k
+        else:
+            assert torch.equal(a, b), k
