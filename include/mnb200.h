@@ -39,6 +39,14 @@ extern "C" {
 #define MNB_LAYOUT_NCHW_F32 1   /* network input: N x C x H x W fp32 (train.py:427) */
 
 int mnb_version(void);
+/* Kernel-selection switches (process-wide; an unset option takes MNB_<NAME> from the environment, then its default):
+ *   "pw_stream" (default 1)  auto routes the low-channel bf16 1x1 layers to the warp-streaming kernels (pw_stream.cu)
+ *   "stem_mma"  (default 1)  auto uses the tensor-pipe stem backward-weight kernel in bf16 mode
+ *   "dw_stream" (default 0)  bf16 depthwise layers use the register row-stream kernels (dwconv_stream.cu) instead of
+ *                            the shared-memory tile kernels
+ * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current 0/1 value or MNB_ERR_ARG. */
+int mnb_set_option(const char* name, int value);
+int mnb_get_option(const char* name);
 const char* mnb_last_error(void);
 /* 1 if the running device is sm_100 (tcgen05 path usable) */
 int mnb_device_is_sm100(void);
@@ -49,7 +57,7 @@ int mnb_device_is_sm100(void);
  * impl: 0 = auto: bf16 1x1 layers with Cin, Cout <= 72 and a packed weight take the warp-streaming mma.sync kernels
  *           (pw_stream.cu; backward-weight needs no packing), everything else bf16 takes tcgen05, fp32 takes SIMT;
  *       1 = force SIMT, 2 = force tcgen05 (bf16), 3 = like auto regardless of MNB_PW_STREAM / MNB_STEM_MMA.
- * MNB_PW_STREAM=0 / MNB_STEM_MMA=0 in the environment keep auto on the tcgen05 / fp32-input stem kernels. */
+ * mnb_set_option("pw_stream" / "stem_mma", 0) keeps auto on the tcgen05 / fp32-input stem kernels. */
 int mnb_conv_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                  void* z, double* stats, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                  int dtype, int x_layout, int impl, void* stream);

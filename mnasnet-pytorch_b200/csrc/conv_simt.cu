@@ -345,15 +345,8 @@ using namespace mnb;
 
 // The warp-streaming kernels of pw_stream.cu take the 1x1 bf16 layers they are instantiated for (measured 2-3x faster
 // than the tcgen05 pipeline on the 112x112 / 56x56 stages, profiles/r1_exp_stream.json) under impl 0 (auto) and impl 3;
-// impl 2 forces tcgen05, impl 1 SIMT.  MNB_PW_STREAM=0 in the environment (read once) switches them off for auto.
-static bool prefer_stream(int impl) {
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("MNB_PW_STREAM");
-        env = (e && e[0] == '0') ? 0 : 1;
-    }
-    return impl == 3 || (impl == 0 && env == 1);
-}
+// impl 2 forces tcgen05, impl 1 SIMT.  mnb_set_option("pw_stream", 0) / MNB_PW_STREAM=0 switch them off for auto.
+static bool prefer_stream(int impl) { return impl == 3 || (impl == 0 && option_get(OPT_PW_STREAM)); }
 
 extern "C" {
 

@@ -277,12 +277,25 @@ static int check_dw(const char* name, int N, int H, int W, int C, int k, int dty
 
 using namespace mnb;
 
+// row-stream kernels (dwconv_stream.cu), selected by the "dw_stream" option
+namespace mnb {
+int dw_fwd_stream(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z,
+                  double* stats, int N, int H, int W, int C, int k, cudaStream_t st);
+int dw_dgrad_stream(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
+int dw_wgrad_stream(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W,
+                    int C, int k, cudaStream_t st);
+}  // namespace mnb
+
 extern "C" {
 
 int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                void* z, double* stats, int N, int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_fwd", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_BF16 && option_get(OPT_DW_STREAM)) {
+        int r = dw_fwd_stream(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16) {
         int r = dw_fwd_tile(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -304,6 +317,10 @@ int mnb_dw_dgrad(const void* dz, const float* w, void* dx, const void* bn_z, con
     MNB_REQUIRE(!bn_z || (bn_scale && bn_shift && bn_sums), "dw_dgrad: bn_z needs bn_scale/bn_shift/bn_sums");
     if (!bn_z) bn_sums = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_BF16 && !bn_z && option_get(OPT_DW_STREAM)) {
+        int r = dw_dgrad_stream(dz, w, dx, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16) {
         int r = dw_dgrad_tile(dz, w, dx, bn_z, bn_scale, bn_shift, bn_sums, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -323,6 +340,10 @@ int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, co
                  int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_wgrad", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_BF16 && option_get(OPT_DW_STREAM)) {
+        int r = dw_wgrad_stream(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16) {
         int r = dw_wgrad_tile(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;

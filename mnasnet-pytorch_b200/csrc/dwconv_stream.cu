@@ -1,0 +1,543 @@
+// Depthwise k x k (3 / 5) stride-1 convolution, bf16 NHWC, as register-resident ROW STREAMS (forward, dgrad, wgrad).
+// Replaces nn.Conv2d(groups=C) (src/models/mnasnet.py:76-81,120-125) with the producing ConvBlock's BN-apply+ReLU
+// fused into the load and this ConvBlock's BN statistics fused into the store, like dwconv_tile.cu -- but with no
+// shared memory, no barriers and no vertical halo:
+//
+//   * a lane owns one channel PAIR (k*k packed fp32x2 weights in registers) and a strip of TW output columns; it
+//     walks DOWN the image: every input row of the strip (TW+k-1 four-byte loads, the next row already in flight)
+//     is transformed once and scattered into the k pending output rows held in a register ring, the completed
+//     output row is rounded, stored and folded into the statistics.  Each input row is therefore loaded and
+//     transformed exactly once per strip (the tile kernel reloads (TH+k-1)/TH of them and pays cp.async address
+//     generation, a shared-memory round trip and two barriers per tile: ~1500 instructions per thread per tile of
+//     which 350 are FFMA2 for 5x5).
+//   * a warp packs G strips x PL channel pairs (PL*G <= 32, PL >= 8 so that a lane group reads whole 32-byte
+//     sectors): all the MNASNet widths except 72 fill 32 lanes (72 channels: 3 strips x 9 pairs = 27 lanes).
+//   * a warp keeps ONE channel block for its whole life (its statistics / weight gradients stay in registers and
+//     are flushed once) and strides over the spatial tasks (image, row segment, strip group).
+//
+// The per-lane program is plain C++ over global pointers (no warp collectives), so the SAME source runs on the
+// host: tests/test_dw_stream_cpu.py builds this file with -DMNB_DW_STREAM_EMUL and checks the lane program, the task
+// decomposition and the padding logic against torch on the CPU before any GPU time is spent.
+#include "common.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define MNB_DEVICE_CODE 1
+#else
+#define MNB_DEVICE_CODE 0
+#endif
+#define MNB_HD __host__ __device__ __forceinline__
+
+namespace mnb {
+
+// ---- packed fp32 pair: one FFMA2 on sm_100, two fmaf on the host --------------------------------------------------
+struct F2 {
+#if MNB_DEVICE_CODE
+    unsigned long long v;
+#else
+    float lo, hi;
+#endif
+};
+MNB_HD F2 f2_make(float lo, float hi) {
+    F2 r;
+#if MNB_DEVICE_CODE
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+#else
+    r.lo = lo; r.hi = hi;
+#endif
+    return r;
+}
+MNB_HD void f2_get(const F2& a, float& lo, float& hi) {
+#if MNB_DEVICE_CODE
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+#else
+    lo = a.lo; hi = a.hi;
+#endif
+}
+MNB_HD F2 f2_fma(const F2& a, const F2& b, const F2& c) {
+    F2 r;
+#if MNB_DEVICE_CODE
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+#else
+    r.lo = fmaf(a.lo, b.lo, c.lo); r.hi = fmaf(a.hi, b.hi, c.hi);
+#endif
+    return r;
+}
+MNB_HD float bits_f(uint32_t u) {
+#if MNB_DEVICE_CODE
+    return __uint_as_float(u);
+#else
+    union { uint32_t i; float f; } c; c.i = u; return c.f;
+#endif
+}
+MNB_HD uint32_t f_bits(float f) {
+#if MNB_DEVICE_CODE
+    return __float_as_uint(f);
+#else
+    union { uint32_t i; float f; } c; c.f = f; return c.i;
+#endif
+}
+MNB_HD F2 f2_from_bf16x2(uint32_t u) { return f2_make(bits_f(u << 16), bits_f(u & 0xffff0000u)); }
+// round-to-nearest-even fp32 -> bf16 (finite inputs; NaN is not produced by this path), packed pair
+MNB_HD uint32_t bf16_rn_bits(float f) {
+    uint32_t u = f_bits(f);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return u >> 16;
+}
+MNB_HD uint32_t pack2_rn(float lo, float hi) {
+#if MNB_DEVICE_CODE
+    return pack_bf16x2(lo, hi);
+#else
+    return bf16_rn_bits(lo) | (bf16_rn_bits(hi) << 16);
+#endif
+}
+MNB_HD uint32_t ld32(const bf16* p) {
+#if MNB_DEVICE_CODE
+    return __ldg(reinterpret_cast<const uint32_t*>(p));
+#else
+    return *reinterpret_cast<const uint32_t*>(p);
+#endif
+}
+
+enum { DWS_FWD = 0, DWS_DGRAD = 1, DWS_WGRAD = 2 };
+
+struct DwSP {
+    const bf16* x;          // fwd / wgrad: input activations (raw conv output of the producer); dgrad: dz
+    const float* in_scale;  // fwd / wgrad: producer BN scale / shift (NULL = raw)
+    const float* in_shift;
+    const float* w;         // [C][k][k]
+    const float* bias;      // fwd, may be NULL
+    const bf16* dz;         // wgrad
+    bf16* out;              // fwd: z ; dgrad: dx
+    float* dw;              // wgrad: [C][k][k], accumulated into
+    double* stats;          // fwd: [2C] sum / sum of squares of the stored values, may be NULL
+    int N, H, W, C;
+    int PL, G;              // channel pairs per lane group, strips per warp (PL * G <= 32)
+    int NB;                 // channel blocks = (C / 2) / PL
+    int HS;                 // output rows per task
+    int nws, nhs;           // strip groups per row = ceil(W / (TW * G)), row segments = ceil(H / HS)
+    int spatial_tasks;      // N * nhs * nws
+    int warps_per_cb;       // warps that share one channel block (task stride)
+};
+
+// what a lane hands to the warp-level flush
+template <int K>
+struct DwLaneOut {
+    float st[4];            // fwd: sum(ch0), sum(ch1), sumsq(ch0), sumsq(ch1)
+    F2 wg[K][K];            // wgrad: dW of the channel pair
+};
+
+// ---- one (image, row segment, strip) of forward / backward-data for one channel pair ------------------------------
+template <int K, int TW, int MODE>
+MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, const F2 (&wr)[K][K], bool xf,
+                          const F2& sc, const F2& sh, float b0, float b1, float (&st)[4]) {
+    constexpr int P = K / 2, NI = TW + K - 1;
+    const int H = p.H, W = p.W, C = p.C;
+    const bf16* xn = p.x + (long long)n * H * W * C + ch;
+    bf16* on = p.out + (long long)n * H * W * C + ch;
+    bool cin_ok[NI], cout_ok[TW];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) { const int col = c0 - P + j; cin_ok[j] = col >= 0 && col < W; }
+#pragma unroll
+    for (int j = 0; j < TW; ++j) cout_ok[j] = c0 + j < W;
+    const F2 zero2 = f2_make(0.f, 0.f);
+    F2 acc[K][TW];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < TW; ++j) acc[i][j] = zero2;
+
+    uint32_t raw[NI];
+    const int first_ir = h0 - P, last_ir = h1 - 1 + P;
+    {
+        const bool rok = first_ir >= 0 && first_ir < H;
+        const bf16* rp = xn + ((long long)first_ir * W + (c0 - P)) * C;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) raw[j] = (rok && cin_ok[j]) ? ld32(rp + (long long)j * C) : 0u;
+    }
+    for (int ir = first_ir; ir <= last_ir; ir += K) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            const int r = ir + u;                      // input row (uniform over the warp)
+            if (r <= last_ir) {
+                uint32_t cur[NI];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) cur[j] = raw[j];
+                if (r + 1 <= last_ir) {                // next row's loads fly while this row is consumed
+                    const bool nok = r + 1 >= 0 && r + 1 < H;
+                    const bf16* rp = xn + ((long long)(r + 1) * W + (c0 - P)) * C;
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) raw[j] = (nok && cin_ok[j]) ? ld32(rp + (long long)j * C) : 0u;
+                }
+                const bool rok = r >= 0 && r < H;
+                F2 in[NI];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    F2 v = f2_from_bf16x2(cur[j]);
+                    if (MODE == DWS_FWD && xf) {
+                        v = f2_fma(sc, v, sh);
+                        float a, b;
+                        f2_get(v, a, b);
+                        // zero padding is applied AFTER the activation (the conv pads the activated tensor)
+                        const bool ok = rok && cin_ok[j];
+                        v = f2_make(ok ? fmaxf(a, 0.f) : 0.f, ok ? fmaxf(b, 0.f) : 0.f);
+                    }
+                    in[j] = v;
+                }
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh) {
+                    const int o = r + P - kh;          // output row fed by this input row through kernel row kh
+                    if (o >= h0 && o < h1) {
+                        const int slot = (u - kh + 2 * K) % K;        // (o - h0) % K, static after unrolling
+#pragma unroll
+                        for (int tc = 0; tc < TW; ++tc)
+#pragma unroll
+                            for (int kw = 0; kw < K; ++kw) acc[slot][tc] = f2_fma(in[tc + kw], wr[kh][kw], acc[slot][tc]);
+                    }
+                }
+                const int od = r - P;                  // output row completed by this input row (kernel row K-1)
+                if (od >= h0 && od < h1) {
+                    const int slot = (u + 1) % K;      // (u - (K-1) + 2K) % K
+                    bf16* orow = on + ((long long)od * W + c0) * C;
+#pragma unroll
+                    for (int tc = 0; tc < TW; ++tc) {
+                        float v0, v1;
+                        f2_get(acc[slot][tc], v0, v1);
+                        acc[slot][tc] = zero2;
+                        if (cout_ok[tc]) {
+                            const uint32_t pk = pack2_rn(v0 + b0, v1 + b1);
+                            *reinterpret_cast<uint32_t*>(orow + (long long)tc * C) = pk;
+                            if (MODE == DWS_FWD) {
+                                const float q0 = bits_f(pk << 16), q1 = bits_f(pk & 0xffff0000u);
+                                st[0] += q0; st[1] += q1;
+                                st[2] = fmaf(q0, q0, st[2]); st[3] = fmaf(q1, q1, st[3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- one (image, row segment, strip) of backward-weight for one channel pair ---------------------------------------
+template <int K, int TW>
+MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, F2 (&wg)[K][K], bool xf, const F2& sc,
+                           const F2& sh) {
+    constexpr int P = K / 2, NI = TW + K - 1;
+    const int H = p.H, W = p.W, C = p.C;
+    const bf16* xn = p.x + (long long)n * H * W * C + ch;
+    const bf16* gn = p.dz + (long long)n * H * W * C + ch;
+    bool cin_ok[NI], cout_ok[TW];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) { const int col = c0 - P + j; cin_ok[j] = col >= 0 && col < W; }
+#pragma unroll
+    for (int j = 0; j < TW; ++j) cout_ok[j] = c0 + j < W;
+    const F2 zero2 = f2_make(0.f, 0.f);
+    F2 g[K][TW];                                       // ring of dz rows, slot = (row - h0) % K
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < TW; ++j) g[i][j] = zero2;
+
+    const int first_ir = h0 - P, last_ir = h1 - 1 + P;
+    for (int ir = first_ir; ir <= last_ir; ir += K) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            const int r = ir + u;                      // input row
+            if (r <= last_ir) {
+                // dz row r + P enters the ring (kernel row 0 pairs it with this input row): slot (u) % K
+                {
+                    const int o = r + P;
+                    const bool ook = o >= h0 && o < h1;
+                    const bf16* rp = gn + ((long long)o * W + c0) * C;
+#pragma unroll
+                    for (int tc = 0; tc < TW; ++tc)
+                        g[u][tc] = (ook && cout_ok[tc]) ? f2_from_bf16x2(ld32(rp + (long long)tc * C)) : zero2;
+                }
+                const bool rok = r >= 0 && r < H;
+                F2 in[NI];
+                {
+                    const bf16* rp = xn + ((long long)r * W + (c0 - P)) * C;
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) {
+                        const bool ok = rok && cin_ok[j];
+                        F2 v = ok ? f2_from_bf16x2(ld32(rp + (long long)j * C)) : zero2;
+                        if (xf) {
+                            v = f2_fma(sc, v, sh);
+                            float a, b;
+                            f2_get(v, a, b);
+                            v = f2_make(ok ? fmaxf(a, 0.f) : 0.f, ok ? fmaxf(b, 0.f) : 0.f);
+                        }
+                        in[j] = v;
+                    }
+                }
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh) {
+                    const int o = r + P - kh;          // dz row paired with this input row through kernel row kh
+                    if (o >= h0 && o < h1) {
+                        const int slot = (u - kh + 2 * K) % K;
+#pragma unroll
+                        for (int tc = 0; tc < TW; ++tc)
+#pragma unroll
+                            for (int kw = 0; kw < K; ++kw) wg[kh][kw] = f2_fma(in[tc + kw], g[slot][tc], wg[kh][kw]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- the whole life of one lane ------------------------------------------------------------------------------------
+template <int K, int TW, int MODE>
+MNB_HD void dws_lane(const DwSP& p, int warp_global, int lane, DwLaneOut<K>& out) {
+    const F2 zero2 = f2_make(0.f, 0.f);
+    out.st[0] = out.st[1] = out.st[2] = out.st[3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) out.wg[i][j] = zero2;
+    const int cb = warp_global % p.NB, widx = warp_global / p.NB;
+    const int gi = lane / p.PL, pl = lane - gi * p.PL;
+    if (gi >= p.G || widx >= p.warps_per_cb) return;
+    const int ch = (cb * p.PL + pl) * 2;
+    const bool xf = (MODE != DWS_DGRAD) && p.in_scale != nullptr;
+    F2 sc = f2_make(1.f, 1.f), sh = zero2;
+    if (xf) { sc = f2_make(p.in_scale[ch], p.in_scale[ch + 1]); sh = f2_make(p.in_shift[ch], p.in_shift[ch + 1]); }
+    float b0 = 0.f, b1 = 0.f;
+    if (MODE == DWS_FWD && p.bias) { b0 = p.bias[ch]; b1 = p.bias[ch + 1]; }
+    F2 wr[K][K];
+    if (MODE != DWS_WGRAD) {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                // backward-data correlates dz with the 180-degree rotated kernel
+                const int ii = MODE == DWS_DGRAD ? K - 1 - i : i, jj = MODE == DWS_DGRAD ? K - 1 - j : j;
+                wr[i][j] = f2_make(p.w[(ch + 0) * K * K + ii * K + jj], p.w[(ch + 1) * K * K + ii * K + jj]);
+            }
+    }
+    const int per_img = p.nhs * p.nws;
+    for (int task = widx; task < p.spatial_tasks; task += p.warps_per_cb) {
+        const int n = task / per_img, rem = task - n * per_img;
+        const int hs = rem / p.nws, ws = rem - hs * p.nws;
+        const int c0 = (ws * p.G + gi) * TW;
+        if (c0 >= p.W) continue;
+        const int h0 = hs * p.HS;
+        int h1 = h0 + p.HS;
+        if (h1 > p.H) h1 = p.H;
+        if (MODE == DWS_WGRAD) dws_wgrad_task<K, TW>(p, n, h0, h1, c0, ch, out.wg, xf, sc, sh);
+        else dws_conv_task<K, TW, MODE>(p, n, h0, h1, c0, ch, wr, xf, sc, sh, b0, b1, out.st);
+    }
+}
+
+// ---- device kernel ---------------------------------------------------------------------------------------------------
+template <int K, int TW, int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) dw_stream_k(const DwSP p) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    DwLaneOut<K> o;
+    dws_lane<K, TW, MODE>(p, warp_global, lane, o);
+    // sum the G strips of a channel pair into lane group 0 (every lane takes part in the shuffles)
+    const int pl = lane % p.PL;
+    if (MODE == DWS_FWD) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v = o.st[q], s = v;
+            for (int gi = 1; gi < p.G; ++gi) s += __shfl_sync(0xffffffffu, v, pl + gi * p.PL);
+            o.st[q] = s;
+        }
+    }
+    if (MODE == DWS_WGRAD) {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                float a, b;
+                f2_get(o.wg[i][j], a, b);
+                float sa = a, sb = b;
+                for (int gi = 1; gi < p.G; ++gi) {
+                    sa += __shfl_sync(0xffffffffu, a, pl + gi * p.PL);
+                    sb += __shfl_sync(0xffffffffu, b, pl + gi * p.PL);
+                }
+                o.wg[i][j] = f2_make(sa, sb);
+            }
+    }
+    const int cb = warp_global % p.NB;
+    if (lane < p.PL && warp_global / p.NB < p.warps_per_cb) {
+        const int ch = (cb * p.PL + lane) * 2;
+        if (MODE == DWS_FWD && p.stats) {
+            atomicAdd(&p.stats[ch], (double)o.st[0]);
+            atomicAdd(&p.stats[ch + 1], (double)o.st[1]);
+            atomicAdd(&p.stats[p.C + ch], (double)o.st[2]);
+            atomicAdd(&p.stats[p.C + ch + 1], (double)o.st[3]);
+        }
+        if (MODE == DWS_WGRAD) {
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    float a, b;
+                    f2_get(o.wg[i][j], a, b);
+                    atomicAdd(&p.dw[(ch + 0) * K * K + i * K + j], a);
+                    atomicAdd(&p.dw[(ch + 1) * K * K + i * K + j], b);
+                }
+        }
+    }
+}
+
+// ---- host side: geometry ---------------------------------------------------------------------------------------------
+// lanes: the largest PL * G <= 32 with PL | C/2 and PL >= 8 (whole 32-byte sectors per lane group); ties -> fewer
+// wasted columns at the right edge, then larger PL
+static bool dws_geometry(DwSP& p, int TW, int total_warps) {
+    const int P2 = p.C / 2;
+    int best_pl = 0, best_g = 0;
+    double best_cost = 1e30;
+    for (int pl = 8; pl <= 32; ++pl) {
+        if (P2 % pl) continue;
+        for (int g = 1; g * pl <= 32 && g <= 4; ++g) {
+            const int cols = TW * g;
+            const double cover = (double)((p.W + cols - 1) / cols) * cols / p.W;      // column over-coverage
+            const double cost = cover * 32.0 / (pl * g) - 1e-3 * pl;
+            if (cost < best_cost) { best_cost = cost; best_pl = pl; best_g = g; }
+        }
+    }
+    if (!best_pl) return false;
+    p.PL = best_pl; p.G = best_g; p.NB = P2 / best_pl;
+    p.nws = (p.W + TW * p.G - 1) / (TW * p.G);
+    p.warps_per_cb = total_warps / p.NB;
+    if (p.warps_per_cb < 1) return false;
+    // row segments: as long as possible (no vertical halo) while every warp still gets >= ~6 tasks
+    int hs = p.H;
+    while (hs > 14) {
+        const long long tasks = (long long)p.N * ((p.H + hs - 1) / hs) * p.nws;
+        if (tasks >= 6ll * p.warps_per_cb) break;
+        hs = (hs + 1) / 2;
+    }
+    p.HS = hs;
+    p.nhs = (p.H + hs - 1) / hs;
+    const long long st = (long long)p.N * p.nhs * p.nws;
+    if (st >= (1ll << 31) || (long long)p.N * p.H * p.W >= (1ll << 31)) return false;
+    p.spatial_tasks = (int)st;
+    return true;
+}
+
+template <int K, int TW, int MODE, int MINB>
+static int dws_launch(DwSP p, cudaStream_t st, const char* name) {
+    const int blocks = num_sms() * MINB;               // 128-thread CTAs: MINB = 4 -> 128 registers per lane, 3 -> 168
+    if (!dws_geometry(p, TW, blocks * 4)) { set_error("%s: shape not covered by the row-stream kernel", name); return MNB_ERR_UNSUPPORTED; }
+    dw_stream_k<K, TW, MODE, MINB><<<blocks, 128, 0, st>>>(p);
+    MNB_LAUNCH_CHECK(name);
+    return 0;
+}
+
+static bool dws_shape_ok(int C, int k) { return (k == 3 || k == 5) && C % 2 == 0; }   // lane packing: dws_geometry
+
+int dw_fwd_stream(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z,
+                  double* stats, int N, int H, int W, int C, int k, cudaStream_t st) {
+    if (!dws_shape_ok(C, k)) { set_error("dw_fwd(stream): C=%d k=%d not covered", C, k); return MNB_ERR_UNSUPPORTED; }
+    DwSP p = {};
+    p.x = (const bf16*)x; p.in_scale = s; p.in_shift = t; p.w = w; p.bias = bias; p.out = (bf16*)z; p.stats = stats;
+    p.N = N; p.H = H; p.W = W; p.C = C;
+    if (k == 3) return dws_launch<3, 4, DWS_FWD, 4>(p, st, "dw_fwd(stream)");
+    return dws_launch<5, 4, DWS_FWD, 3>(p, st, "dw_fwd(stream)");
+}
+int dw_dgrad_stream(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st) {
+    if (!dws_shape_ok(C, k)) { set_error("dw_dgrad(stream): C=%d k=%d not covered", C, k); return MNB_ERR_UNSUPPORTED; }
+    DwSP p = {};
+    p.x = (const bf16*)dz; p.w = w; p.out = (bf16*)dx;
+    p.N = N; p.H = H; p.W = W; p.C = C;
+    if (k == 3) return dws_launch<3, 4, DWS_DGRAD, 4>(p, st, "dw_dgrad(stream)");
+    return dws_launch<5, 4, DWS_DGRAD, 3>(p, st, "dw_dgrad(stream)");
+}
+int dw_wgrad_stream(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W,
+                    int C, int k, cudaStream_t st) {
+    if (!dws_shape_ok(C, k)) { set_error("dw_wgrad(stream): C=%d k=%d not covered", C, k); return MNB_ERR_UNSUPPORTED; }
+    DwSP p = {};
+    p.x = (const bf16*)x; p.in_scale = s; p.in_shift = t; p.dz = (const bf16*)dz; p.dw = dw;
+    p.N = N; p.H = H; p.W = W; p.C = C;
+    if (k == 3) return dws_launch<3, 4, DWS_WGRAD, 4>(p, st, "dw_wgrad(stream)");
+    return dws_launch<5, 2, DWS_WGRAD, 3>(p, st, "dw_wgrad(stream)");
+}
+
+}  // namespace mnb
+
+// ---- host emulation of the lane program (test infrastructure; compiled only with -DMNB_DW_STREAM_EMUL) -------------------
+#if defined(MNB_DW_STREAM_EMUL) && !defined(__CUDA_ARCH__)
+namespace mnb {
+void set_error(const char*, ...) {}
+// flush of one lane's results after lane group 0 collected its G strips (mirrors the tail of dw_stream_k)
+template <int K, int MODE>
+static void dws_flush_lane(const DwSP& p, int warp_global, int lane, const DwLaneOut<K>& o,
+                           void (*add_f64)(double*, double), void (*add_f32)(float*, float)) {
+    const int cb = warp_global % p.NB;
+    if (lane >= p.PL || warp_global / p.NB >= p.warps_per_cb) return;
+    const int ch = (cb * p.PL + lane) * 2;
+    if (MODE == DWS_FWD && p.stats) {
+        add_f64(&p.stats[ch], (double)o.st[0]);
+        add_f64(&p.stats[ch + 1], (double)o.st[1]);
+        add_f64(&p.stats[p.C + ch], (double)o.st[2]);
+        add_f64(&p.stats[p.C + ch + 1], (double)o.st[3]);
+    }
+    if (MODE == DWS_WGRAD) {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                float a, b;
+                f2_get(o.wg[i][j], a, b);
+                add_f32(&p.dw[(ch + 0) * K * K + i * K + j], a);
+                add_f32(&p.dw[(ch + 1) * K * K + i * K + j], b);
+            }
+    }
+}
+
+static void emul_add_f64(double* p, double v) { *p += v; }
+static void emul_add_f32(float* p, float v) { *p += v; }
+
+template <int K, int TW, int MODE>
+static int emul_run(DwSP p, int total_warps) {
+    if (!dws_geometry(p, TW, total_warps)) return MNB_ERR_UNSUPPORTED;
+    for (int wgl = 0; wgl < total_warps; ++wgl) {
+        DwLaneOut<K> lanes[32];
+        for (int lane = 0; lane < 32; ++lane) dws_lane<K, TW, MODE>(p, wgl, lane, lanes[lane]);
+        // what the shuffles do: lane group 0 collects the strips of its channel pair
+        for (int pl = 0; pl < p.PL; ++pl)
+            for (int gi = 1; gi < p.G; ++gi) {
+                const DwLaneOut<K>& s = lanes[pl + gi * p.PL];
+                for (int q = 0; q < 4; ++q) lanes[pl].st[q] += s.st[q];
+                for (int i = 0; i < K; ++i)
+                    for (int j = 0; j < K; ++j) {
+                        lanes[pl].wg[i][j].lo += s.wg[i][j].lo;
+                        lanes[pl].wg[i][j].hi += s.wg[i][j].hi;
+                    }
+            }
+        for (int lane = 0; lane < 32; ++lane) dws_flush_lane<K, MODE>(p, wgl, lane, lanes[lane], emul_add_f64, emul_add_f32);
+    }
+    return 0;
+}
+}  // namespace mnb
+
+// all pointers are HOST pointers; mode 0 fwd / 1 dgrad / 2 wgrad; geometry[6] returns PL, G, NB, HS, nws, nhs
+extern "C" int mnb_emul_dw_stream(int mode, const void* x, const float* s, const float* t, const float* w,
+                                  const float* bias, const void* dz, void* out, float* dw, double* stats, int N, int H,
+                                  int W, int C, int k, int total_warps, int* geometry) {
+    using namespace mnb;
+    DwSP p = {};
+    p.x = (const bf16*)x; p.in_scale = s; p.in_shift = t; p.w = w; p.bias = bias; p.dz = (const bf16*)dz;
+    p.out = (bf16*)out; p.dw = dw; p.stats = stats; p.N = N; p.H = H; p.W = W; p.C = C;
+    if (geometry) {
+        DwSP q = p;
+        const int tw = (mode == 2 && k == 5) ? 2 : 4;
+        if (!dws_geometry(q, tw, total_warps)) return MNB_ERR_UNSUPPORTED;
+        geometry[0] = q.PL; geometry[1] = q.G; geometry[2] = q.NB; geometry[3] = q.HS; geometry[4] = q.nws; geometry[5] = q.nhs;
+    }
+    if (k == 3) {
+        if (mode == 0) return emul_run<3, 4, DWS_FWD>(p, total_warps);
+        if (mode == 1) return emul_run<3, 4, DWS_DGRAD>(p, total_warps);
+        return emul_run<3, 4, DWS_WGRAD>(p, total_warps);
+    }
+    if (mode == 0) return emul_run<5, 4, DWS_FWD>(p, total_warps);
+    if (mode == 1) return emul_run<5, 4, DWS_DGRAD>(p, total_warps);
+    return emul_run<5, 2, DWS_WGRAD>(p, total_warps);
+}
+#endif

@@ -4,6 +4,8 @@
 // per-CTA shared-memory partials flushed with one fp64 atomic per channel per CTA.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -15,6 +17,19 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// kernel-selection switches: -1 = not set yet (the environment variable is consulted once, then the built-in default)
+static int g_opt[OPT_COUNT] = {-1, -1, -1};
+static const char* const g_opt_name[OPT_COUNT] = {"pw_stream", "stem_mma", "dw_stream"};
+static const char* const g_opt_env[OPT_COUNT] = {"MNB_PW_STREAM", "MNB_STEM_MMA", "MNB_DW_STREAM"};
+static const int g_opt_default[OPT_COUNT] = {1, 1, 0};
+int option_get(int id) {
+    if (g_opt[id] < 0) {
+        const char* e = getenv(g_opt_env[id]);
+        g_opt[id] = e ? (e[0] != '0' ? 1 : 0) : g_opt_default[id];
+    }
+    return g_opt[id];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -587,6 +602,18 @@ using namespace mnb;
 extern "C" {
 
 int mnb_version(void) { return 100; }
+int mnb_set_option(const char* name, int value) {
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (!strcmp(name, g_opt_name[i])) { g_opt[i] = value ? 1 : 0; return 0; }
+    set_error("set_option: unknown option '%s'", name);
+    return MNB_ERR_ARG;
+}
+int mnb_get_option(const char* name) {
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (!strcmp(name, g_opt_name[i])) return option_get(i);
+    set_error("get_option: unknown option '%s'", name);
+    return MNB_ERR_ARG;
+}
 const char* mnb_last_error(void) { return g_err; }
 int mnb_device_is_sm100(void) {
     int dev = 0, major = 0;

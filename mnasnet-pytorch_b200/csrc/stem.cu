@@ -299,12 +299,8 @@ int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, i
     const long long cap = (long long)num_sms() * 4;
     if (blocks > cap) blocks = cap;
     // bf16: tensor-pipe kernel (11x faster, profiles/r1_exp_stream.json) unless impl 2 asks for the fp32-input SIMT
-    // kernel or MNB_STEM_MMA=0 is set (read once)
-    static int use_mma = -1;
-    if (use_mma < 0) {
-        const char* e = getenv("MNB_STEM_MMA");
-        use_mma = (e && e[0] == '0') ? 0 : 1;
-    }
+    // kernel or the "stem_mma" option / MNB_STEM_MMA is 0
+    const int use_mma = option_get(OPT_STEM_MMA);
     if (dtype == MNB_BF16 && (impl == 3 || (impl == 0 && use_mma)) && total < (1ll << 31) - 64) {
         stem_wgrad_mma_k<<<num_sms() * 4, 128, 0, st>>>(x, (const bf16*)dz, dw, N, H, W, Ho, Wo);
         MNB_LAUNCH_CHECK("stem_wgrad(mma)");

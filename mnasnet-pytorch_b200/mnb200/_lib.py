@@ -84,6 +84,18 @@ def call(name, *args):
     check(getattr(lib, name)(*args), name)
 
 
+def set_option(name: str, value: int):
+    """Process-wide kernel-selection switch ("pw_stream", "stem_mma", "dw_stream"; include/mnb200.h)."""
+    check(lib.mnb_set_option(name.encode(), int(value)), "set_option")
+
+
+def get_option(name: str) -> int:
+    v = lib.mnb_get_option(name.encode())
+    if v < 0:
+        check(v, "get_option")
+    return v
+
+
 def ptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
