@@ -42,9 +42,10 @@ int mnb_version(void);
 /* Kernel-selection switches (process-wide; an unset option takes MNB_<NAME> from the environment, then its default):
  *   "pw_stream" (default 1)  auto routes the low-channel bf16 1x1 layers to the warp-streaming kernels (pw_stream.cu)
  *   "stem_mma"  (default 1)  auto uses the tensor-pipe stem backward-weight kernel in bf16 mode
- *   "dw_stream" (default 0)  bf16 depthwise layers use the register row-stream kernels (dwconv_stream.cu) instead of
- *                            the shared-memory tile kernels
- * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current 0/1 value or MNB_ERR_ARG. */
+ *   "dw_stream" (default 2)  bf16 depthwise layers: 0 = shared-memory tile kernels only, 1 = register row-stream
+ *                            kernels (dwconv_stream.cu) everywhere, 2 = row-stream where it measured faster (maps of
+ *                            <= 7 rows; 5x5 forward / backward-data on maps of >= 56 rows)
+ * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current value or MNB_ERR_ARG. */
 int mnb_set_option(const char* name, int value);
 int mnb_get_option(const char* name);
 const char* mnb_last_error(void);

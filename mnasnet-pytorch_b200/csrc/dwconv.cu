@@ -277,8 +277,16 @@ static int check_dw(const char* name, int N, int H, int W, int C, int k, int dty
 
 using namespace mnb;
 
-// row-stream kernels (dwconv_stream.cu), selected by the "dw_stream" option
+// row-stream kernels (dwconv_stream.cu), selected by the "dw_stream" option: 0 = never, 1 = always, 2 = where they
+// measured faster than the tile kernels on B200 (profiles/r1_exp_dw_stream.json): 7x7-and-smaller maps (all three
+// passes) and the 5x5 layers on >= 56-row maps (forward and backward-data; their backward-weight is slower)
 namespace mnb {
+static bool use_dw_stream(int pass /*0 fwd, 1 dgrad, 2 wgrad*/, int H, int k) {
+    const int o = option_get(OPT_DW_STREAM);
+    if (o == 1) return true;
+    if (o != 2) return false;
+    return H <= 7 || (k == 5 && H >= 56 && pass != 2);
+}
 int dw_fwd_stream(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z,
                   double* stats, int N, int H, int W, int C, int k, cudaStream_t st);
 int dw_dgrad_stream(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
@@ -292,7 +300,7 @@ int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, cons
                void* z, double* stats, int N, int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_fwd", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MNB_BF16 && option_get(OPT_DW_STREAM)) {
+    if (dtype == MNB_BF16 && use_dw_stream(0, H, k)) {
         int r = dw_fwd_stream(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
@@ -317,7 +325,7 @@ int mnb_dw_dgrad(const void* dz, const float* w, void* dx, const void* bn_z, con
     MNB_REQUIRE(!bn_z || (bn_scale && bn_shift && bn_sums), "dw_dgrad: bn_z needs bn_scale/bn_shift/bn_sums");
     if (!bn_z) bn_sums = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MNB_BF16 && !bn_z && option_get(OPT_DW_STREAM)) {
+    if (dtype == MNB_BF16 && !bn_z && use_dw_stream(1, H, k)) {
         int r = dw_dgrad_stream(dz, w, dx, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
@@ -340,7 +348,7 @@ int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, co
                  int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_wgrad", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MNB_BF16 && option_get(OPT_DW_STREAM)) {
+    if (dtype == MNB_BF16 && use_dw_stream(2, H, k)) {
         int r = dw_wgrad_stream(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }

@@ -23,11 +23,11 @@ void set_error(const char* fmt, ...) {
 static int g_opt[OPT_COUNT] = {-1, -1, -1};
 static const char* const g_opt_name[OPT_COUNT] = {"pw_stream", "stem_mma", "dw_stream"};
 static const char* const g_opt_env[OPT_COUNT] = {"MNB_PW_STREAM", "MNB_STEM_MMA", "MNB_DW_STREAM"};
-static const int g_opt_default[OPT_COUNT] = {1, 1, 0};
+static const int g_opt_default[OPT_COUNT] = {1, 1, 2};
 int option_get(int id) {
     if (g_opt[id] < 0) {
         const char* e = getenv(g_opt_env[id]);
-        g_opt[id] = e ? (e[0] != '0' ? 1 : 0) : g_opt_default[id];
+        g_opt[id] = e ? atoi(e) : g_opt_default[id];
     }
     return g_opt[id];
 }
@@ -604,7 +604,7 @@ extern "C" {
 int mnb_version(void) { return 100; }
 int mnb_set_option(const char* name, int value) {
     for (int i = 0; i < OPT_COUNT; ++i)
-        if (!strcmp(name, g_opt_name[i])) { g_opt[i] = value ? 1 : 0; return 0; }
+        if (!strcmp(name, g_opt_name[i])) { g_opt[i] = value < 0 ? 0 : value; return 0; }
     set_error("set_option: unknown option '%s'", name);
     return MNB_ERR_ARG;
 }

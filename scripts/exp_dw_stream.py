@@ -102,7 +102,7 @@ def layer_case(N, H, C, k):
         out[f"fwd_us_{tag}"] = round(timeit(f_fwd), 1)
         out[f"dgrad_us_{tag}"] = round(timeit(f_dg), 1)
         out[f"wgrad_us_{tag}"] = round(timeit(f_wg), 1)
-    L.set_option("dw_stream", 0)
+    L.set_option("dw_stream", 2)
     z1, st1, dx1, dw1 = res[1]
     z0, st0, dx0, dw0 = res[0]
     out["nan"] = int(torch.isnan(z1.float()).sum().item() + torch.isnan(dx1.float()).sum().item())
@@ -121,7 +121,7 @@ def net_case(n_big, steps):
     xb = torch.randn(n_big, 3, 224, 224, device=dev)
     tb = torch.randint(0, 1000, (n_big,), device=dev)
     big = {}
-    for opt in (0, 1):
+    for opt in (0, 1, 2):
         L.set_option("dw_stream", opt)              # graphs captured now keep the kernels selected now
         torch.manual_seed(42)
         m = FineTuneModelPool(load_model('mnasnet'), 'mnasnet', 1000, '512')
@@ -139,14 +139,14 @@ def net_case(n_big, steps):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        tag = "stream" if opt else "tile"
+        tag = ("tile", "stream", "auto")[opt]
         big[f"ms_per_step_{tag}"] = round(ms, 3)
         big[f"img_per_s_{tag}"] = round(n_big / ms * 1e3, 1)
         big[f"loss_first_{tag}"] = first
         big[f"loss_last_{tag}"] = l.item()
         del eng, m
         torch.cuda.empty_cache()
-    L.set_option("dw_stream", 0)
+    L.set_option("dw_stream", 2)
     item("net_big", **big)
 
 

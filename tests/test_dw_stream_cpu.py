@@ -61,6 +61,11 @@ CASES = [
     (1, 33, 17, 16, 3, True, 40),       # more warps than tasks -> short row segments, idle warps
     (3, 14, 14, 64, 5, False, 5),
     (1, 5, 6, 1152, 3, True, 36),
+    (2, 2, 2, 1152, 3, True, 592),      # tiny maps of the progressive-resize shapes, full-size grid
+    (2, 4, 4, 576, 5, True, 444),
+    (1, 3, 4, 480, 3, False, 592),
+    (1, 1, 1, 240, 5, True, 444),
+    (2, 64, 48, 72, 5, True, 444),      # rectangular cluster crop at the 5x5 / 72-channel layer
 ]
 
 
