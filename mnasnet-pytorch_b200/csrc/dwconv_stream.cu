@@ -127,7 +127,8 @@ struct DwLaneOut {
 };
 
 // ---- one (image, row segment, strip) of forward / backward-data for one channel pair ------------------------------
-template <int K, int TW, int MODE>
+// PD = how many input rows ahead of the one being consumed are already in flight
+template <int K, int TW, int MODE, int PD>
 MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, const F2 (&wr)[K][K], bool xf,
                           const F2& sc, const F2& sh, float b0, float b1, float (&st)[4]) {
     constexpr int P = K / 2, NI = TW + K - 1;
@@ -146,14 +147,16 @@ MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, 
 #pragma unroll
         for (int j = 0; j < TW; ++j) acc[i][j] = zero2;
 
-    uint32_t raw[NI];
+    uint32_t raw[PD][NI];
     const int first_ir = h0 - P, last_ir = h1 - 1 + P;
-    {
-        const bool rok = first_ir >= 0 && first_ir < H;
-        const bf16* rp = xn + ((long long)first_ir * W + (c0 - P)) * C;
+    auto load_row = [&](int rr, uint32_t (&dst)[NI]) {
+        const bool rok = rr >= 0 && rr < H && rr <= last_ir;
+        const bf16* rp = xn + ((long long)rr * W + (c0 - P)) * C;
 #pragma unroll
-        for (int j = 0; j < NI; ++j) raw[j] = (rok && cin_ok[j]) ? ld32(rp + (long long)j * C) : 0u;
-    }
+        for (int j = 0; j < NI; ++j) dst[j] = (rok && cin_ok[j]) ? ld32(rp + (long long)j * C) : 0u;
+    };
+#pragma unroll
+    for (int d = 0; d < PD; ++d) load_row(first_ir + d, raw[d]);
     for (int ir = first_ir; ir <= last_ir; ir += K) {
 #pragma unroll
         for (int u = 0; u < K; ++u) {
@@ -161,13 +164,12 @@ MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, 
             if (r <= last_ir) {
                 uint32_t cur[NI];
 #pragma unroll
-                for (int j = 0; j < NI; ++j) cur[j] = raw[j];
-                if (r + 1 <= last_ir) {                // next row's loads fly while this row is consumed
-                    const bool nok = r + 1 >= 0 && r + 1 < H;
-                    const bf16* rp = xn + ((long long)(r + 1) * W + (c0 - P)) * C;
+                for (int j = 0; j < NI; ++j) cur[j] = raw[0][j];
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) raw[j] = (nok && cin_ok[j]) ? ld32(rp + (long long)j * C) : 0u;
-                }
+                for (int d = 0; d + 1 < PD; ++d)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) raw[d][j] = raw[d + 1][j];
+                load_row(r + PD, raw[PD - 1]);         // row r+PD's loads fly while rows r .. r+PD-1 are consumed
                 const bool rok = r >= 0 && r < H;
                 F2 in[NI];
 #pragma unroll
@@ -220,7 +222,7 @@ MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, 
 }
 
 // ---- one (image, row segment, strip) of backward-weight for one channel pair ---------------------------------------
-template <int K, int TW>
+template <int K, int TW, int PD>
 MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, F2 (&wg)[K][K], bool xf, const F2& sc,
                            const F2& sh) {
     constexpr int P = K / 2, NI = TW + K - 1;
@@ -240,28 +242,46 @@ MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch,
         for (int j = 0; j < TW; ++j) g[i][j] = zero2;
 
     const int first_ir = h0 - P, last_ir = h1 - 1 + P;
+    uint32_t rawx[PD][NI], rawg[PD][TW];               // input row rr and dz row rr + P, PD rows ahead
+    auto load_rows = [&](int rr, uint32_t (&dx)[NI], uint32_t (&dg)[TW]) {
+        const bool rok = rr >= 0 && rr < H && rr <= last_ir;
+        const bf16* rp = xn + ((long long)rr * W + (c0 - P)) * C;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dx[j] = (rok && cin_ok[j]) ? ld32(rp + (long long)j * C) : 0u;
+        const int o = rr + P;
+        const bool ook = o >= h0 && o < h1 && rr <= last_ir;
+        const bf16* gp = gn + ((long long)o * W + c0) * C;
+#pragma unroll
+        for (int tc = 0; tc < TW; ++tc) dg[tc] = (ook && cout_ok[tc]) ? ld32(gp + (long long)tc * C) : 0u;
+    };
+#pragma unroll
+    for (int d = 0; d < PD; ++d) load_rows(first_ir + d, rawx[d], rawg[d]);
     for (int ir = first_ir; ir <= last_ir; ir += K) {
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             const int r = ir + u;                      // input row
             if (r <= last_ir) {
+                uint32_t curx[NI];
                 // dz row r + P enters the ring (kernel row 0 pairs it with this input row): slot (u) % K
-                {
-                    const int o = r + P;
-                    const bool ook = o >= h0 && o < h1;
-                    const bf16* rp = gn + ((long long)o * W + c0) * C;
 #pragma unroll
-                    for (int tc = 0; tc < TW; ++tc)
-                        g[u][tc] = (ook && cout_ok[tc]) ? f2_from_bf16x2(ld32(rp + (long long)tc * C)) : zero2;
+                for (int tc = 0; tc < TW; ++tc) g[u][tc] = f2_from_bf16x2(rawg[0][tc]);
+#pragma unroll
+                for (int j = 0; j < NI; ++j) curx[j] = rawx[0][j];
+#pragma unroll
+                for (int d = 0; d + 1 < PD; ++d) {
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) rawx[d][j] = rawx[d + 1][j];
+#pragma unroll
+                    for (int tc = 0; tc < TW; ++tc) rawg[d][tc] = rawg[d + 1][tc];
                 }
+                load_rows(r + PD, rawx[PD - 1], rawg[PD - 1]);
                 const bool rok = r >= 0 && r < H;
                 F2 in[NI];
                 {
-                    const bf16* rp = xn + ((long long)r * W + (c0 - P)) * C;
 #pragma unroll
                     for (int j = 0; j < NI; ++j) {
                         const bool ok = rok && cin_ok[j];
-                        F2 v = ok ? f2_from_bf16x2(ld32(rp + (long long)j * C)) : zero2;
+                        F2 v = f2_from_bf16x2(curx[j]);
                         if (xf) {
                             v = f2_fma(sc, v, sh);
                             float a, b;
@@ -288,7 +308,7 @@ MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch,
 }
 
 // ---- the whole life of one lane ------------------------------------------------------------------------------------
-template <int K, int TW, int MODE>
+template <int K, int TW, int MODE, int PD>
 MNB_HD void dws_lane(const DwSP& p, int warp_global, int lane, DwLaneOut<K>& out) {
     const F2 zero2 = f2_make(0.f, 0.f);
     out.st[0] = out.st[1] = out.st[2] = out.st[3] = 0.f;
@@ -325,18 +345,18 @@ MNB_HD void dws_lane(const DwSP& p, int warp_global, int lane, DwLaneOut<K>& out
         const int h0 = hs * p.HS;
         int h1 = h0 + p.HS;
         if (h1 > p.H) h1 = p.H;
-        if (MODE == DWS_WGRAD) dws_wgrad_task<K, TW>(p, n, h0, h1, c0, ch, out.wg, xf, sc, sh);
-        else dws_conv_task<K, TW, MODE>(p, n, h0, h1, c0, ch, wr, xf, sc, sh, b0, b1, out.st);
+        if (MODE == DWS_WGRAD) dws_wgrad_task<K, TW, PD>(p, n, h0, h1, c0, ch, out.wg, xf, sc, sh);
+        else dws_conv_task<K, TW, MODE, PD>(p, n, h0, h1, c0, ch, wr, xf, sc, sh, b0, b1, out.st);
     }
 }
 
 // ---- device kernel ---------------------------------------------------------------------------------------------------
-template <int K, int TW, int MODE, int MINB>
+template <int K, int TW, int MODE, int PD, int MINB>
 __global__ void __launch_bounds__(128, MINB) dw_stream_k(const DwSP p) {
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     DwLaneOut<K> o;
-    dws_lane<K, TW, MODE>(p, warp_global, lane, o);
+    dws_lane<K, TW, MODE, PD>(p, warp_global, lane, o);
     // sum the G strips of a channel pair into lane group 0 (every lane takes part in the shuffles)
     const int pl = lane % p.PL;
     if (MODE == DWS_FWD) {
@@ -425,7 +445,10 @@ template <int K, int TW, int MODE, int MINB>
 static int dws_launch(DwSP p, cudaStream_t st, const char* name) {
     const int blocks = num_sms() * MINB;               // 128-thread CTAs: MINB = 4 -> 128 registers per lane, 3 -> 168
     if (!dws_geometry(p, TW, blocks * 4)) { set_error("%s: shape not covered by the row-stream kernel", name); return MNB_ERR_UNSUPPORTED; }
-    dw_stream_k<K, TW, MODE, MINB><<<blocks, 128, 0, st>>>(p);
+    const int pd = option_get(OPT_DW_STREAM_PD);       // rows of prefetch (1..3), see include/mnb200.h
+    if (pd >= 3) dw_stream_k<K, TW, MODE, 3, MINB><<<blocks, 128, 0, st>>>(p);
+    else if (pd == 2) dw_stream_k<K, TW, MODE, 2, MINB><<<blocks, 128, 0, st>>>(p);
+    else dw_stream_k<K, TW, MODE, 1, MINB><<<blocks, 128, 0, st>>>(p);
     MNB_LAUNCH_CHECK(name);
     return 0;
 }
@@ -465,6 +488,7 @@ int dw_wgrad_stream(const void* x, const float* s, const float* t, const void* d
 #if defined(MNB_DW_STREAM_EMUL) && !defined(__CUDA_ARCH__)
 namespace mnb {
 void set_error(const char*, ...) {}
+int option_get(int) { return 1; }
 // flush of one lane's results after lane group 0 collected its G strips (mirrors the tail of dw_stream_k)
 template <int K, int MODE>
 static void dws_flush_lane(const DwSP& p, int warp_global, int lane, const DwLaneOut<K>& o,
@@ -494,12 +518,12 @@ static void dws_flush_lane(const DwSP& p, int warp_global, int lane, const DwLan
 static void emul_add_f64(double* p, double v) { *p += v; }
 static void emul_add_f32(float* p, float v) { *p += v; }
 
-template <int K, int TW, int MODE>
-static int emul_run(DwSP p, int total_warps) {
+template <int K, int TW, int MODE, int PD>
+static int emul_run_pd(DwSP p, int total_warps) {
     if (!dws_geometry(p, TW, total_warps)) return MNB_ERR_UNSUPPORTED;
     for (int wgl = 0; wgl < total_warps; ++wgl) {
         DwLaneOut<K> lanes[32];
-        for (int lane = 0; lane < 32; ++lane) dws_lane<K, TW, MODE>(p, wgl, lane, lanes[lane]);
+        for (int lane = 0; lane < 32; ++lane) dws_lane<K, TW, MODE, PD>(p, wgl, lane, lanes[lane]);
         // what the shuffles do: lane group 0 collects the strips of its channel pair
         for (int pl = 0; pl < p.PL; ++pl)
             for (int gi = 1; gi < p.G; ++gi) {
@@ -516,6 +540,17 @@ static int emul_run(DwSP p, int total_warps) {
     return 0;
 }
 }  // namespace mnb
+
+namespace mnb {
+static int g_emul_pd = 1;
+template <int K, int TW, int MODE>
+static int emul_run(const DwSP& p, int total_warps) {
+    if (g_emul_pd >= 3) return emul_run_pd<K, TW, MODE, 3>(p, total_warps);
+    if (g_emul_pd == 2) return emul_run_pd<K, TW, MODE, 2>(p, total_warps);
+    return emul_run_pd<K, TW, MODE, 1>(p, total_warps);
+}
+}  // namespace mnb
+extern "C" void mnb_emul_dw_stream_set_pd(int pd) { mnb::g_emul_pd = pd; }
 
 // all pointers are HOST pointers; mode 0 fwd / 1 dgrad / 2 wgrad; geometry[6] returns PL, G, NB, HS, nws, nhs
 extern "C" int mnb_emul_dw_stream(int mode, const void* x, const float* s, const float* t, const float* w,

@@ -80,8 +80,9 @@ def layer_case(N, H, C, k):
     sh = (torch.randn(C, device=dev, generator=g) * 0.3).float()
     out = {"shape": f"{N}x{H}x{W}x{C} k{k}", "bytes_fwd": 2 * x.numel() * 2}
     res = {}
-    for opt in (0, 1):
+    for tag, opt, pd in (("tile", 0, 1), ("stream", 1, 1), ("stream_pd2", 1, 2), ("stream_pd3", 1, 3)):
         L.set_option("dw_stream", opt)
+        L.set_option("dw_stream_pd", pd)
         z = torch.full_like(x, float("nan"))
         st = torch.zeros(2 * C, device=dev, dtype=torch.float64)
         dx = torch.full_like(x, float("nan"))
@@ -97,21 +98,21 @@ def layer_case(N, H, C, k):
             L.call("mnb_dw_wgrad", P(x), P(sc), P(sh), P(dz), P(dw), N, H, W, C, k, 1, S())
         f_fwd(); f_dg(); f_wg()
         torch.cuda.synchronize()
-        res[opt] = (z.clone(), st.clone(), dx.clone(), dw.clone())
-        tag = "stream" if opt else "tile"
+        res[tag] = (z.clone(), st.clone(), dx.clone(), dw.clone())
         out[f"fwd_us_{tag}"] = round(timeit(f_fwd), 1)
         out[f"dgrad_us_{tag}"] = round(timeit(f_dg), 1)
         out[f"wgrad_us_{tag}"] = round(timeit(f_wg), 1)
     L.set_option("dw_stream", 2)
-    z1, st1, dx1, dw1 = res[1]
-    z0, st0, dx0, dw0 = res[0]
-    out["nan"] = int(torch.isnan(z1.float()).sum().item() + torch.isnan(dx1.float()).sum().item())
-    out["fwd_rel"] = relerr(z1.float(), z0.float())
-    out["stats_rel"] = relerr(st1, st0)
-    out["dgrad_rel"] = relerr(dx1.float(), dx0.float())
-    out["wgrad_rel"] = relerr(dw1, dw0)
-    out["ok"] = bool(out["nan"] == 0 and out["fwd_rel"] < 5e-3 and out["dgrad_rel"] < 5e-3 and out["wgrad_rel"] < 5e-3
-                     and out["stats_rel"] < 5e-3)
+    L.set_option("dw_stream_pd", 1)
+    z0, st0, dx0, dw0 = res["tile"]
+    ok = True
+    for tag in ("stream", "stream_pd2", "stream_pd3"):
+        z1, st1, dx1, dw1 = res[tag]
+        nan = int(torch.isnan(z1.float()).sum().item() + torch.isnan(dx1.float()).sum().item())
+        rels = (relerr(z1.float(), z0.float()), relerr(st1, st0), relerr(dx1.float(), dx0.float()), relerr(dw1, dw0))
+        out[f"rel_{tag}"] = [float(f"{r:.2e}") for r in rels]          # fwd, stats, dgrad, wgrad
+        ok = ok and nan == 0 and all(r < 5e-3 for r in rels)
+    out["ok"] = bool(ok)
     return out
 
 
@@ -121,8 +122,9 @@ def net_case(n_big, steps):
     xb = torch.randn(n_big, 3, 224, 224, device=dev)
     tb = torch.randint(0, 1000, (n_big,), device=dev)
     big = {}
-    for opt in (0, 1, 2):
+    for opt, pd in ((0, 1), (1, 1), (2, 1), (1, 3), (2, 3)):
         L.set_option("dw_stream", opt)              # graphs captured now keep the kernels selected now
+        L.set_option("dw_stream_pd", pd)
         torch.manual_seed(42)
         m = FineTuneModelPool(load_model('mnasnet'), 'mnasnet', 1000, '512')
         engine.configure(m, dtype="bf16")
@@ -139,7 +141,7 @@ def net_case(n_big, steps):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        tag = ("tile", "stream", "auto")[opt]
+        tag = ("tile", "stream", "auto")[opt] + (f"_pd{pd}" if pd > 1 else "")
         big[f"ms_per_step_{tag}"] = round(ms, 3)
         big[f"img_per_s_{tag}"] = round(n_big / ms * 1e3, 1)
         big[f"loss_first_{tag}"] = first
@@ -147,6 +149,7 @@ def net_case(n_big, steps):
         del eng, m
         torch.cuda.empty_cache()
     L.set_option("dw_stream", 2)
+    L.set_option("dw_stream_pd", 1)
     item("net_big", **big)
 
 

@@ -39,6 +39,9 @@ def emul():
     fn = lib.mnb_emul_dw_stream
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 9 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    fn.set_pd = lib.mnb_emul_dw_stream_set_pd
+    fn.set_pd.argtypes = [ctypes.c_int]
+    fn.set_pd.restype = None
     return fn
 
 
@@ -69,9 +72,11 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("pd", [1, 2, 3])
 @pytest.mark.parametrize("case", CASES)
-def test_lane_program_matches_torch(emul, case):
+def test_lane_program_matches_torch(emul, case, pd):
     N, H, W, C, k, xform, warps = case
+    emul.set_pd(pd)                                    # rows of prefetch kept in flight (option "dw_stream_pd")
     g = torch.Generator().manual_seed(N * 100 + H + C)
     x = torch.randn(N, H, W, C, generator=g).to(torch.bfloat16)
     w = (torch.randn(C, 1, k, k, generator=g) / k).float()

@@ -163,5 +163,6 @@ def test_kernel_selection_options():
     _lib.set_option("dw_stream", 0)
     assert _lib.get_option("dw_stream") == 0
     _lib.set_option("dw_stream", 2)
+    assert _lib.get_option("dw_stream_pd") == 1
     with pytest.raises(_lib.MnbError):
         _lib.set_option("no_such_option", 1)
