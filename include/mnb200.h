@@ -43,8 +43,8 @@ int mnb_version(void);
  *   "pw_stream" (default 1)  auto routes the low-channel bf16 1x1 layers to the warp-streaming kernels (pw_stream.cu)
  *   "stem_mma"  (default 1)  auto uses the tensor-pipe stem backward-weight kernel in bf16 mode
  *   "dw_stream" (default 2)  bf16 depthwise layers: 0 = shared-memory tile kernels only, 1 = register row-stream
- *                            kernels (dwconv_stream.cu) everywhere, 2 = row-stream where it measured faster (maps of
- *                            <= 7 rows; 5x5 forward / backward-data on maps of >= 56 rows)
+ *                            kernels (dwconv_stream.cu) everywhere, 2 = row-stream where it measured faster
+ *                            (forward / backward-data on maps of <= 7 rows and of the 5x5 layers on >= 56 rows)
  *   "dw_stream_pd" (default 1)  input rows the row-stream kernels keep in flight ahead of the one they consume (1..3;
  *                            2 and 3 are untimed experiments: more memory-level parallelism, more registers)
  * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current value or MNB_ERR_ARG. */

@@ -278,14 +278,14 @@ static int check_dw(const char* name, int N, int H, int W, int C, int k, int dty
 using namespace mnb;
 
 // row-stream kernels (dwconv_stream.cu), selected by the "dw_stream" option: 0 = never, 1 = always, 2 = where they
-// measured faster than the tile kernels on B200 (profiles/r1_exp_dw_stream.json): 7x7-and-smaller maps (all three
-// passes) and the 5x5 layers on >= 56-row maps (forward and backward-data; their backward-weight is slower)
+// measured faster than the tile kernels on B200 (profiles/r1_exp_dw_stream.json): forward and backward-data of
+// 7x7-and-smaller maps and of the 5x5 layers on >= 56-row maps (backward-weight stays on the tile kernels)
 namespace mnb {
 static bool use_dw_stream(int pass /*0 fwd, 1 dgrad, 2 wgrad*/, int H, int k) {
     const int o = option_get(OPT_DW_STREAM);
     if (o == 1) return true;
     if (o != 2) return false;
-    return H <= 7 || (k == 5 && H >= 56 && pass != 2);
+    return pass != 2 && (H <= 7 || (k == 5 && H >= 56));
 }
 int dw_fwd_stream(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z,
                   double* stats, int N, int H, int W, int C, int k, cudaStream_t st);
