@@ -127,64 +127,92 @@ struct DwLaneOut {
 };
 
 // ---- one (image, row segment, strip) of forward / backward-data for one channel pair ------------------------------
-// PD = how many input rows ahead of the one being consumed are already in flight
-template <int K, int TW, int MODE, int PD>
-MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, const F2 (&wr)[K][K], bool xf,
-                          const F2& sc, const F2& sh, float b0, float b1, float (&st)[4]) {
+// All addressing is 32-bit element offsets from the tensor base (the host checks N*H*W*C < 2^31): one running row
+// offset plus the per-lane constants jC[j] = j*C.  EDGE = the warp's strips touch the left / right image border (then
+// every column access is predicated by a bit mask); interior warps take the unpredicated variant: only the row
+// validity is tested, and that is uniform over the warp.  PD = input rows in flight ahead of the one being consumed.
+template <int K, int TW, int MODE, int PD, bool EDGE>
+MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, const int (&jC)[TW + K - 1],
+                          const F2 (&wr)[K][K], bool xf, const F2& sc, const F2& sh, float b0, float b1, F2& ssum,
+                          F2& ssq) {
     constexpr int P = K / 2, NI = TW + K - 1;
-    const int H = p.H, W = p.W, C = p.C;
-    const bf16* xn = p.x + (long long)n * H * W * C + ch;
-    bf16* on = p.out + (long long)n * H * W * C + ch;
-    bool cin_ok[NI], cout_ok[TW];
+    const int H = p.H, W = p.W;
+    const int rs = W * p.C;                             // row stride in elements
+    unsigned cmask = (1u << NI) - 1u, omask = (1u << TW) - 1u;
+    if (EDGE) {
+        cmask = 0u; omask = 0u;
 #pragma unroll
-    for (int j = 0; j < NI; ++j) { const int col = c0 - P + j; cin_ok[j] = col >= 0 && col < W; }
+        for (int j = 0; j < NI; ++j) { const int col = c0 - P + j; if (col >= 0 && col < W) cmask |= 1u << j; }
 #pragma unroll
-    for (int j = 0; j < TW; ++j) cout_ok[j] = c0 + j < W;
-    const F2 zero2 = f2_make(0.f, 0.f);
+        for (int j = 0; j < TW; ++j) if (c0 + j < W) omask |= 1u << j;
+    }
+    const F2 zero2 = f2_make(0.f, 0.f), one2 = f2_make(1.f, 1.f);
     F2 acc[K][TW];
 #pragma unroll
     for (int i = 0; i < K; ++i)
 #pragma unroll
         for (int j = 0; j < TW; ++j) acc[i][j] = zero2;
 
-    uint32_t raw[PD][NI];
     const int first_ir = h0 - P, last_ir = h1 - 1 + P;
-    auto load_row = [&](int rr, uint32_t (&dst)[NI]) {
+    // offsets of (row, column c0-P) of the input and (row, column c0) of the output; positions outside the image
+    // are never dereferenced
+    int off_next = ((n * H + first_ir) * W + (c0 - P)) * p.C + ch;
+    int ooff = ((n * H + h0) * W + c0) * p.C + ch;
+    uint32_t raw[PD][NI];
+    auto load_row = [&](int rr, int roff, uint32_t (&dst)[NI]) {
         const bool rok = rr >= 0 && rr < H && rr <= last_ir;
-        const bf16* rp = xn + ((long long)rr * W + (c0 - P)) * C;
+        if (EDGE) {
 #pragma unroll
-        for (int j = 0; j < NI; ++j) dst[j] = (rok && cin_ok[j]) ? ld32(rp + (long long)j * C) : 0u;
+            for (int j = 0; j < NI; ++j) dst[j] = (rok && ((cmask >> j) & 1u)) ? ld32(p.x + (roff + jC[j])) : 0u;
+        } else if (rok) {
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dst[j] = ld32(p.x + (roff + jC[j]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dst[j] = 0u;
+        }
     };
 #pragma unroll
-    for (int d = 0; d < PD; ++d) load_row(first_ir + d, raw[d]);
+    for (int d = 0; d < PD; ++d) { load_row(first_ir + d, off_next, raw[d]); off_next += rs; }
     for (int ir = first_ir; ir <= last_ir; ir += K) {
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             const int r = ir + u;                      // input row (uniform over the warp)
             if (r <= last_ir) {
-                uint32_t cur[NI];
+                const bool rok = r >= 0 && r < H;
+                F2 in[NI];
+                if (MODE == DWS_FWD && xf) {
+                    // zero padding is applied AFTER the activation (the conv pads the activated tensor)
+                    if (EDGE) {
 #pragma unroll
-                for (int j = 0; j < NI; ++j) cur[j] = raw[0][j];
+                        for (int j = 0; j < NI; ++j) {
+                            float a, b;
+                            f2_get(f2_fma(sc, f2_from_bf16x2(raw[0][j]), sh), a, b);
+                            const bool ok = rok && ((cmask >> j) & 1u);
+                            in[j] = f2_make(ok ? fmaxf(a, 0.f) : 0.f, ok ? fmaxf(b, 0.f) : 0.f);
+                        }
+                    } else if (rok) {
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) {
+                            float a, b;
+                            f2_get(f2_fma(sc, f2_from_bf16x2(raw[0][j]), sh), a, b);
+                            in[j] = f2_make(fmaxf(a, 0.f), fmaxf(b, 0.f));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) in[j] = zero2;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) in[j] = f2_from_bf16x2(raw[0][j]);       // invalid positions hold 0
+                }
+                // raw[0] is consumed: shift the ring and put row r+PD in flight
 #pragma unroll
                 for (int d = 0; d + 1 < PD; ++d)
 #pragma unroll
                     for (int j = 0; j < NI; ++j) raw[d][j] = raw[d + 1][j];
-                load_row(r + PD, raw[PD - 1]);         // row r+PD's loads fly while rows r .. r+PD-1 are consumed
-                const bool rok = r >= 0 && r < H;
-                F2 in[NI];
-#pragma unroll
-                for (int j = 0; j < NI; ++j) {
-                    F2 v = f2_from_bf16x2(cur[j]);
-                    if (MODE == DWS_FWD && xf) {
-                        v = f2_fma(sc, v, sh);
-                        float a, b;
-                        f2_get(v, a, b);
-                        // zero padding is applied AFTER the activation (the conv pads the activated tensor)
-                        const bool ok = rok && cin_ok[j];
-                        v = f2_make(ok ? fmaxf(a, 0.f) : 0.f, ok ? fmaxf(b, 0.f) : 0.f);
-                    }
-                    in[j] = v;
-                }
+                load_row(r + PD, off_next, raw[PD - 1]);
+                off_next += rs;
 #pragma unroll
                 for (int kh = 0; kh < K; ++kh) {
                     const int o = r + P - kh;          // output row fed by this input row through kernel row kh
@@ -199,22 +227,22 @@ MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, 
                 const int od = r - P;                  // output row completed by this input row (kernel row K-1)
                 if (od >= h0 && od < h1) {
                     const int slot = (u + 1) % K;      // (u - (K-1) + 2K) % K
-                    bf16* orow = on + ((long long)od * W + c0) * C;
 #pragma unroll
                     for (int tc = 0; tc < TW; ++tc) {
                         float v0, v1;
                         f2_get(acc[slot][tc], v0, v1);
                         acc[slot][tc] = zero2;
-                        if (cout_ok[tc]) {
+                        if (!EDGE || ((omask >> tc) & 1u)) {
                             const uint32_t pk = pack2_rn(v0 + b0, v1 + b1);
-                            *reinterpret_cast<uint32_t*>(orow + (long long)tc * C) = pk;
-                            if (MODE == DWS_FWD) {
-                                const float q0 = bits_f(pk << 16), q1 = bits_f(pk & 0xffff0000u);
-                                st[0] += q0; st[1] += q1;
-                                st[2] = fmaf(q0, q0, st[2]); st[3] = fmaf(q1, q1, st[3]);
+                            *reinterpret_cast<uint32_t*>(p.out + (ooff + jC[tc])) = pk;
+                            if (MODE == DWS_FWD) {     // statistics of the stored (rounded) values
+                                const F2 q = f2_from_bf16x2(pk);
+                                ssum = f2_fma(q, one2, ssum);
+                                ssq = f2_fma(q, q, ssq);
                             }
                         }
                     }
+                    ooff += rs;
                 }
             }
         }
@@ -222,18 +250,20 @@ MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, 
 }
 
 // ---- one (image, row segment, strip) of backward-weight for one channel pair ---------------------------------------
-template <int K, int TW, int PD>
-MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, F2 (&wg)[K][K], bool xf, const F2& sc,
-                           const F2& sh) {
+template <int K, int TW, int PD, bool EDGE>
+MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, const int (&jC)[TW + K - 1],
+                           F2 (&wg)[K][K], bool xf, const F2& sc, const F2& sh) {
     constexpr int P = K / 2, NI = TW + K - 1;
-    const int H = p.H, W = p.W, C = p.C;
-    const bf16* xn = p.x + (long long)n * H * W * C + ch;
-    const bf16* gn = p.dz + (long long)n * H * W * C + ch;
-    bool cin_ok[NI], cout_ok[TW];
+    const int H = p.H, W = p.W;
+    const int rs = W * p.C;
+    unsigned cmask = (1u << NI) - 1u, omask = (1u << TW) - 1u;
+    if (EDGE) {
+        cmask = 0u; omask = 0u;
 #pragma unroll
-    for (int j = 0; j < NI; ++j) { const int col = c0 - P + j; cin_ok[j] = col >= 0 && col < W; }
+        for (int j = 0; j < NI; ++j) { const int col = c0 - P + j; if (col >= 0 && col < W) cmask |= 1u << j; }
 #pragma unroll
-    for (int j = 0; j < TW; ++j) cout_ok[j] = c0 + j < W;
+        for (int j = 0; j < TW; ++j) if (c0 + j < W) omask |= 1u << j;
+    }
     const F2 zero2 = f2_make(0.f, 0.f);
     F2 g[K][TW];                                       // ring of dz rows, slot = (row - h0) % K
 #pragma unroll
@@ -242,31 +272,74 @@ MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch,
         for (int j = 0; j < TW; ++j) g[i][j] = zero2;
 
     const int first_ir = h0 - P, last_ir = h1 - 1 + P;
-    uint32_t rawx[PD][NI], rawg[PD][TW];               // input row rr and dz row rr + P, PD rows ahead
-    auto load_rows = [&](int rr, uint32_t (&dx)[NI], uint32_t (&dg)[TW]) {
+    int xoff_next = ((n * H + first_ir) * W + (c0 - P)) * p.C + ch;      // input row rr, column c0-P
+    int goff_next = ((n * H + first_ir + P) * W + c0) * p.C + ch;        // dz row rr+P, column c0
+    uint32_t rawx[PD][NI], rawg[PD][TW];
+    auto load_rows = [&](int rr, int xoff, int goff, uint32_t (&dx)[NI], uint32_t (&dg)[TW]) {
         const bool rok = rr >= 0 && rr < H && rr <= last_ir;
-        const bf16* rp = xn + ((long long)rr * W + (c0 - P)) * C;
-#pragma unroll
-        for (int j = 0; j < NI; ++j) dx[j] = (rok && cin_ok[j]) ? ld32(rp + (long long)j * C) : 0u;
         const int o = rr + P;
         const bool ook = o >= h0 && o < h1 && rr <= last_ir;
-        const bf16* gp = gn + ((long long)o * W + c0) * C;
+        if (EDGE) {
 #pragma unroll
-        for (int tc = 0; tc < TW; ++tc) dg[tc] = (ook && cout_ok[tc]) ? ld32(gp + (long long)tc * C) : 0u;
+            for (int j = 0; j < NI; ++j) dx[j] = (rok && ((cmask >> j) & 1u)) ? ld32(p.x + (xoff + jC[j])) : 0u;
+#pragma unroll
+            for (int tc = 0; tc < TW; ++tc) dg[tc] = (ook && ((omask >> tc) & 1u)) ? ld32(p.dz + (goff + jC[tc])) : 0u;
+        } else {
+            if (rok) {
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dx[j] = ld32(p.x + (xoff + jC[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dx[j] = 0u;
+            }
+            if (ook) {
+#pragma unroll
+                for (int tc = 0; tc < TW; ++tc) dg[tc] = ld32(p.dz + (goff + jC[tc]));
+            } else {
+#pragma unroll
+                for (int tc = 0; tc < TW; ++tc) dg[tc] = 0u;
+            }
+        }
     };
 #pragma unroll
-    for (int d = 0; d < PD; ++d) load_rows(first_ir + d, rawx[d], rawg[d]);
+    for (int d = 0; d < PD; ++d) {
+        load_rows(first_ir + d, xoff_next, goff_next, rawx[d], rawg[d]);
+        xoff_next += rs; goff_next += rs;
+    }
     for (int ir = first_ir; ir <= last_ir; ir += K) {
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             const int r = ir + u;                      // input row
             if (r <= last_ir) {
-                uint32_t curx[NI];
-                // dz row r + P enters the ring (kernel row 0 pairs it with this input row): slot (u) % K
+                const bool rok = r >= 0 && r < H;
+                // dz row r + P enters the ring (kernel row 0 pairs it with this input row): slot u
 #pragma unroll
                 for (int tc = 0; tc < TW; ++tc) g[u][tc] = f2_from_bf16x2(rawg[0][tc]);
+                F2 in[NI];
+                if (xf) {
+                    if (EDGE) {
 #pragma unroll
-                for (int j = 0; j < NI; ++j) curx[j] = rawx[0][j];
+                        for (int j = 0; j < NI; ++j) {
+                            float a, b;
+                            f2_get(f2_fma(sc, f2_from_bf16x2(rawx[0][j]), sh), a, b);
+                            const bool ok = rok && ((cmask >> j) & 1u);
+                            in[j] = f2_make(ok ? fmaxf(a, 0.f) : 0.f, ok ? fmaxf(b, 0.f) : 0.f);
+                        }
+                    } else if (rok) {
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) {
+                            float a, b;
+                            f2_get(f2_fma(sc, f2_from_bf16x2(rawx[0][j]), sh), a, b);
+                            in[j] = f2_make(fmaxf(a, 0.f), fmaxf(b, 0.f));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) in[j] = zero2;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) in[j] = f2_from_bf16x2(rawx[0][j]);
+                }
 #pragma unroll
                 for (int d = 0; d + 1 < PD; ++d) {
 #pragma unroll
@@ -274,23 +347,8 @@ MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch,
 #pragma unroll
                     for (int tc = 0; tc < TW; ++tc) rawg[d][tc] = rawg[d + 1][tc];
                 }
-                load_rows(r + PD, rawx[PD - 1], rawg[PD - 1]);
-                const bool rok = r >= 0 && r < H;
-                F2 in[NI];
-                {
-#pragma unroll
-                    for (int j = 0; j < NI; ++j) {
-                        const bool ok = rok && cin_ok[j];
-                        F2 v = f2_from_bf16x2(curx[j]);
-                        if (xf) {
-                            v = f2_fma(sc, v, sh);
-                            float a, b;
-                            f2_get(v, a, b);
-                            v = f2_make(ok ? fmaxf(a, 0.f) : 0.f, ok ? fmaxf(b, 0.f) : 0.f);
-                        }
-                        in[j] = v;
-                    }
-                }
+                load_rows(r + PD, xoff_next, goff_next, rawx[PD - 1], rawg[PD - 1]);
+                xoff_next += rs; goff_next += rs;
 #pragma unroll
                 for (int kh = 0; kh < K; ++kh) {
                     const int o = r + P - kh;          // dz row paired with this input row through kernel row kh
@@ -310,6 +368,7 @@ MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch,
 // ---- the whole life of one lane ------------------------------------------------------------------------------------
 template <int K, int TW, int MODE, int PD>
 MNB_HD void dws_lane(const DwSP& p, int warp_global, int lane, DwLaneOut<K>& out) {
+    constexpr int P = K / 2, NI = TW + K - 1;
     const F2 zero2 = f2_make(0.f, 0.f);
     out.st[0] = out.st[1] = out.st[2] = out.st[3] = 0.f;
 #pragma unroll
@@ -336,18 +395,31 @@ MNB_HD void dws_lane(const DwSP& p, int warp_global, int lane, DwLaneOut<K>& out
                 wr[i][j] = f2_make(p.w[(ch + 0) * K * K + ii * K + jj], p.w[(ch + 1) * K * K + ii * K + jj]);
             }
     }
+    int jC[NI];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) jC[j] = j * p.C;
+    F2 ssum = zero2, ssq = zero2;
     const int per_img = p.nhs * p.nws;
     for (int task = widx; task < p.spatial_tasks; task += p.warps_per_cb) {
         const int n = task / per_img, rem = task - n * per_img;
         const int hs = rem / p.nws, ws = rem - hs * p.nws;
         const int c0 = (ws * p.G + gi) * TW;
-        if (c0 >= p.W) continue;
         const int h0 = hs * p.HS;
         int h1 = h0 + p.HS;
         if (h1 > p.H) h1 = p.H;
-        if (MODE == DWS_WGRAD) dws_wgrad_task<K, TW, PD>(p, n, h0, h1, c0, ch, out.wg, xf, sc, sh);
-        else dws_conv_task<K, TW, MODE, PD>(p, n, h0, h1, c0, ch, wr, xf, sc, sh, b0, b1, out.st);
+        // uniform over the warp: do this warp's strips (columns [ws*G*TW, (ws+1)*G*TW) plus the halo) touch a border?
+        const bool edge = ws == 0 || (ws + 1) * p.G * TW + P > p.W;
+        if (edge) {
+            if (c0 >= p.W) continue;
+            if (MODE == DWS_WGRAD) dws_wgrad_task<K, TW, PD, true>(p, n, h0, h1, c0, ch, jC, out.wg, xf, sc, sh);
+            else dws_conv_task<K, TW, MODE, PD, true>(p, n, h0, h1, c0, ch, jC, wr, xf, sc, sh, b0, b1, ssum, ssq);
+        } else {
+            if (MODE == DWS_WGRAD) dws_wgrad_task<K, TW, PD, false>(p, n, h0, h1, c0, ch, jC, out.wg, xf, sc, sh);
+            else dws_conv_task<K, TW, MODE, PD, false>(p, n, h0, h1, c0, ch, jC, wr, xf, sc, sh, b0, b1, ssum, ssq);
+        }
     }
+    f2_get(ssum, out.st[0], out.st[1]);
+    f2_get(ssq, out.st[2], out.st[3]);
 }
 
 // ---- device kernel ---------------------------------------------------------------------------------------------------
@@ -436,7 +508,8 @@ static bool dws_geometry(DwSP& p, int TW, int total_warps) {
     p.HS = hs;
     p.nhs = (p.H + hs - 1) / hs;
     const long long st = (long long)p.N * p.nhs * p.nws;
-    if (st >= (1ll << 31) || (long long)p.N * p.H * p.W >= (1ll << 31)) return false;
+    // 32-bit element offsets inside the kernel (one extra row of slack for the prefetch offsets)
+    if (st >= (1ll << 31) || ((long long)p.N * p.H + 8) * p.W * p.C >= (1ll << 31)) return false;
     p.spatial_tasks = (int)st;
     return true;
 }

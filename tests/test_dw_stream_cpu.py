@@ -69,6 +69,9 @@ CASES = [
     (1, 3, 4, 480, 3, False, 592),
     (1, 1, 1, 240, 5, True, 444),
     (2, 64, 48, 72, 5, True, 444),      # rectangular cluster crop at the 5x5 / 72-channel layer
+    (1, 9, 70, 32, 3, True, 16),        # wide maps: interior (unpredicated) strips between the two border strips
+    (2, 20, 100, 48, 5, True, 24),
+    (1, 12, 66, 16, 3, False, 10),
 ]
 
 
