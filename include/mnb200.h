@@ -42,7 +42,7 @@ int mnb_version(void);
 /* Kernel-selection switches (process-wide; an unset option takes MNB_<NAME> from the environment, then its default):
  *   "pw_stream" (default 1)  auto routes the low-channel bf16 1x1 layers to the warp-streaming kernels (pw_stream.cu)
  *   "stem_mma"  (default 1)  auto uses the tensor-pipe stem backward-weight kernel in bf16 mode
- *   "dw_stream" (default 2)  bf16 depthwise layers: 0 = shared-memory tile kernels only, 1 = register row-stream
+ *   "dw_stream" (default 0)  bf16 depthwise layers: 0 = shared-memory tile kernels only, 1 = register row-stream
  *                            kernels (dwconv_stream.cu) everywhere, 2 = row-stream where it measured faster
  *                            (forward / backward-data on maps of <= 7 rows and of the 5x5 layers on >= 56 rows)
  *   "dw_stream_pd" (default 1)  input rows the row-stream kernels keep in flight ahead of the one they consume (1..3;

@@ -102,7 +102,7 @@ def layer_case(N, H, C, k):
         out[f"fwd_us_{tag}"] = round(timeit(f_fwd), 1)
         out[f"dgrad_us_{tag}"] = round(timeit(f_dg), 1)
         out[f"wgrad_us_{tag}"] = round(timeit(f_wg), 1)
-    L.set_option("dw_stream", 2)
+    L.set_option("dw_stream", 0)
     L.set_option("dw_stream_pd", 1)
     z0, st0, dx0, dw0 = res["tile"]
     ok = True
@@ -148,7 +148,7 @@ def net_case(n_big, steps):
         big[f"loss_last_{tag}"] = l.item()
         del eng, m
         torch.cuda.empty_cache()
-    L.set_option("dw_stream", 2)
+    L.set_option("dw_stream", 0)
     L.set_option("dw_stream_pd", 1)
     item("net_big", **big)
 

@@ -210,7 +210,7 @@ def test_depthwise_row_stream_kernels(case):
             torch.cuda.synchronize()
             res[opt] = (z, stats, dx, dw)
     finally:
-        ML.set_option("dw_stream", 2)
+        ML.set_option("dw_stream", 0)
     z, stats, dx, dw = res[1]
     assert torch.isfinite(z.float()).all() and torch.isfinite(dx.float()).all()
     assert rel(nchw(z), zref) < TOL["bf16"]
