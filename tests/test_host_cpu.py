@@ -168,3 +168,44 @@ def test_kernel_selection_options():
     assert _lib.get_option("dw_stream_pd") == 1
     with pytest.raises(_lib.MnbError):
         _lib.set_option("no_such_option", 1)
+
+
+def test_lr_regimes_match_torch_and_the_reference_cyclic_lr():
+    import importlib.util
+    from mnb200 import lr as L
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    # ExponentialLR(gamma=0.99), one step per epoch (src/train.py:284-286, 335)
+    opt = torch.optim.Adam(p, lr=1e-3)
+    sch_t = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.99)
+    s = L.Schedule("auto_decay", 1e-3)
+    for _ in range(30):
+        opt.step()
+        sch_t.step()
+        assert abs(s.epoch_step() - opt.param_groups[0]["lr"]) < 1e-15
+    # ReduceLROnPlateau(mode='min', factor=0.5, patience=5) (src/train.py:289-293, 337)
+    opt = torch.optim.Adam(p, lr=1e-3)
+    sch_t = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.5, patience=5)
+    s = L.Schedule("plateau_decay", 1e-3)
+    g = torch.Generator().manual_seed(0)
+    losses = [1.0 / (1 + 0.3 * i) if i < 8 else 0.3 + 0.01 * torch.rand((), generator=g).item() for i in range(60)]
+    for v in losses:
+        sch_t.step(v)
+        assert abs(s.epoch_step(v) - opt.param_groups[0]["lr"]) < 1e-15
+    assert opt.param_groups[0]["lr"] < 1e-3                      # it did decay
+    # CyclicLR exp_range as configured at src/train.py:296-301, against the reference's own class when present
+    path = "/root/reference/src/utils/cyclic_lr.py"
+    if os.path.exists(path):
+        spec = importlib.util.spec_from_file_location("ref_clr", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        opt = torch.optim.Adam(p, lr=1e-3)
+        ref = mod.CyclicLR(optimizer=opt, base_lr=1e-4, max_lr=1e-2, step_size=1200, mode="exp_range", gamma=0.95)
+        s = L.Schedule("clr", 1e-3)
+        assert abs(s.lr - opt.param_groups[0]["lr"]) < 1e-15
+        for _ in range(3000):
+            ref.batch_step()
+            assert abs(s.batch_step() - opt.param_groups[0]["lr"]) < 1e-12
+    assert abs(L.cyclic(600, mode="triangular") - (1e-4 + (1e-2 - 1e-4) * 0.5)) < 1e-15
+    assert L.epoch_decay(1e-3, 48) == 1e-3 and abs(L.epoch_decay(1e-3, 49) - 9e-4) < 1e-18
+    with pytest.raises(ValueError):
+        L.Schedule("nope", 1e-3)
