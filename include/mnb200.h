@@ -187,6 +187,11 @@ int mnb_xent_fwd_bwd(const float* logits, const long long* target, float* loss, 
 int mnb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, int step, float grad_scale, const float* dev_lr, const long long* dev_step,
                   void* stream);
+/* torch.optim.SGD(lr) (momentum 0) and torch.optim.RMSprop(lr) (alpha 0.99, eps 1e-8, not centered, momentum 0):
+ * the other optimizers train.py:222-229 can select.  p -= lr * g  /  sq = alpha*sq + (1-alpha)*g*g; p -= lr*g/(sqrt(sq)+eps) */
+int mnb_sgd_step(float* p, const float* g, long long n, float lr, float grad_scale, const float* dev_lr, void* stream);
+int mnb_rmsprop_step(float* p, const float* g, float* square_avg, long long n, float lr, float alpha, float eps,
+                     float grad_scale, const float* dev_lr, void* stream);
 /* *counter += 1 on the device (step counter feeding mnb_adam_step / mnb_dropout_mask inside a graph) */
 int mnb_counter_inc(long long* counter, void* stream);
 

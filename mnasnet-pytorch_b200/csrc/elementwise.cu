@@ -561,6 +561,27 @@ __global__ void __launch_bounds__(256) adam_k(float* __restrict__ p, const float
     }
 }
 
+// torch.optim.SGD (momentum 0) and torch.optim.RMSprop (alpha 0.99, not centered, momentum 0) over a flat buffer:
+// the other two optimizers src/train.py:222-229 can select
+__global__ void __launch_bounds__(256) sgd_k(float* __restrict__ p, const float* __restrict__ g, long long n, float lr,
+                                             float gscale, const float* dev_lr) {
+    if (dev_lr) lr = *dev_lr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] -= lr * (g[i] * gscale);
+}
+__global__ void __launch_bounds__(256) rmsprop_k(float* __restrict__ p, const float* __restrict__ g,
+                                                 float* __restrict__ sq, long long n, float lr, float alpha, float eps,
+                                                 float gscale, const float* dev_lr) {
+    if (dev_lr) lr = *dev_lr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float s = sq[i] * alpha + (1.f - alpha) * (gi * gi);      // square_avg.mul_(alpha).addcmul_(g, g, 1-alpha)
+        sq[i] = s;
+        p[i] -= lr * (gi / (sqrtf(s) + eps));                           // param.addcdiv_(g, sqrt(square_avg)+eps, -lr)
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // layout helpers (module-boundary only; not on the fused step's path)
 // ---------------------------------------------------------------------------------------------------
@@ -826,6 +847,21 @@ int mnb_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
     adam_k<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale,
                                                            dev_lr, dev_step);
     MNB_LAUNCH_CHECK("adam");
+    return 0;
+}
+
+int mnb_sgd_step(float* p, const float* g, long long n, float lr, float grad_scale, const float* dev_lr, void* stream) {
+    MNB_REQUIRE(n > 0, "sgd: bad n");
+    sgd_k<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, n, lr, grad_scale, dev_lr);
+    MNB_LAUNCH_CHECK("sgd");
+    return 0;
+}
+
+int mnb_rmsprop_step(float* p, const float* g, float* square_avg, long long n, float lr, float alpha, float eps,
+                     float grad_scale, const float* dev_lr, void* stream) {
+    MNB_REQUIRE(n > 0, "rmsprop: bad n");
+    rmsprop_k<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, square_avg, n, lr, alpha, eps, grad_scale, dev_lr);
+    MNB_LAUNCH_CHECK("rmsprop");
     return 0;
 }
 

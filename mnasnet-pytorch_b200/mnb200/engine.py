@@ -727,6 +727,7 @@ class Engine:
         self.fuse_bn_reduce = False    # BN-backward reductions in the producing dgrad epilogue (tested; off:
                                        # the dgrad epilogues are the bottleneck, the separate kernel is faster)
         self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
+        self.optimizer = "adam"        # 'adam' | 'rmsprop' | 'sgd' (train.py:218-231); set before the first graph capture
 
     def plan(self, N, H, W) -> Plan:
         key = (N, H, W)
@@ -806,8 +807,28 @@ class Engine:
         if self.grad_hook is not None:
             self.grad_hook.wait()
             gscale = 1.0 / self.grad_hook.world
-        self.adam(lr, betas, eps, gscale)
+        self.optimizer_step(lr, betas, eps, gscale)
         return plan.loss
+
+    def optimizer_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, lr_on_device=False):
+        """`optimizer.step()` of the optimizer selected by `Engine.optimizer` (train.py:218-231: 'adam' | 'rmsprop' |
+        'sgd', all with torch's defaults) over the flat parameter / gradient buffers."""
+        if self.optimizer == "adam":
+            return self.adam(lr, betas, eps, grad_scale, lr_on_device)
+        stream = torch.cuda.current_stream().cuda_stream
+        st = self.store
+        dev_lr = self.dev_lr.data_ptr() if lr_on_device else None
+        self.host_step += 1
+        check(lib.mnb_counter_inc(self.dev_step.data_ptr(), stream), "counter_inc")
+        if self.optimizer == "sgd":
+            check(lib.mnb_sgd_step(st.flat.data_ptr(), st.grad.data_ptr(), st.total, float(lr), grad_scale, dev_lr,
+                                   stream), "sgd")
+        elif self.optimizer == "rmsprop":
+            _, v = st.adam_state()              # the second-moment buffer doubles as RMSprop's square_avg
+            check(lib.mnb_rmsprop_step(st.flat.data_ptr(), st.grad.data_ptr(), v.data_ptr(), st.total, float(lr),
+                                       0.99, 1e-8, grad_scale, dev_lr, stream), "rmsprop")
+        else:
+            raise ValueError(f"unknown optimizer {self.optimizer!r}")
 
     def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, lr_on_device=False):
         stream = torch.cuda.current_stream().cuda_stream
@@ -877,7 +898,7 @@ class Engine:
         check(lib.mnb_xent_fwd_bwd(plan.logits.data_ptr(), plan.target.data_ptr(), plan.loss.data_ptr(),
                                    plan.dlogits.data_ptr(), plan.N, plan.num_out, 1.0, stream), "xent")
         self.backward(plan)
-        self.adam(0.0, betas, eps, 1.0, lr_on_device=True)
+        self.optimizer_step(0.0, betas, eps, 1.0, lr_on_device=True)
 
     def launches_per_step(self, N, H, W):
         """Number of libmnb200 kernel launches in one fused training step of this shape."""

@@ -223,3 +223,40 @@ def test_depthwise_row_stream_kernels(case):
     # kernel re-rounds it to bf16), so outputs agree to bf16 rounding, not bit for bit
     z0, stats0, dx0, dw0 = res[0]
     assert rel(z.float(), z0.float()) < 5e-3 and rel(dx.float(), dx0.float()) < 5e-3 and rel(dw, dw0) < 5e-3
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "rmsprop"])
+def test_other_optimizers_match_torch(opt_name):
+    """torch.optim.SGD / RMSprop with the reference's arguments (lr only, train.py:222-229) vs the flat
+    kernels, three steps on random gradients, and through the engine's fused step."""
+    L = _lib()
+    n = 100003
+    g = torch.Generator(device="cuda").manual_seed(3)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = (torch.optim.SGD if opt_name == "sgd" else torch.optim.RMSprop)([ref], lr=1e-2)
+    p = p0.clone()
+    sq = torch.zeros(n, device="cuda")
+    for _ in range(3):
+        grad = torch.randn(n, device="cuda", generator=g) * 0.1
+        ref.grad = grad.clone()
+        opt.step()
+        if opt_name == "sgd":
+            L.call("mnb_sgd_step", P(p), P(grad), n, 1e-2, 1.0, None, stream())
+        else:
+            L.call("mnb_rmsprop_step", P(p), P(grad), P(sq), n, 1e-2, 0.99, 1e-8, 1.0, None, stream())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(p, ref.data, rtol=1e-5, atol=1e-6)
+    # the engine's fused step with that optimizer moves the parameters and keeps the loss finite
+    from mnb200 import engine
+    from oracle import mnasnet_oracle as O
+    m = _build("fp32")
+    eng = engine.engine_for(m)
+    eng.optimizer = opt_name
+    x, t = O.synthetic_batch(2, 64, 64)
+    before = eng.store.flat.clone()
+    l1 = eng.train_step(x.cuda(), t.cuda(), lr=1e-3).item()
+    torch.cuda.synchronize()
+    assert math.isfinite(l1) and not torch.equal(before, eng.store.flat)
+    if opt_name == "sgd":
+        torch.testing.assert_close(eng.store.flat, before - 1e-3 * eng.store.grad, rtol=1e-6, atol=1e-7)
