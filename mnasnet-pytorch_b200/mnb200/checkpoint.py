@@ -121,7 +121,7 @@ def make_checkpoint(module: nn.Module, engine=None, epoch: int = 0, best_loss: f
                     lr: float = 1e-3, parallel_prefix: bool = True):
     """The dict the reference saves at the end of an epoch (src/train.py:380-385).  `epoch` is the NEXT epoch."""
     ck = {"epoch": epoch, "state_dict": reference_state_dict(module, parallel_prefix), "best_loss": best_loss}
-    if engine is not None:
+    if engine is not None and getattr(engine, "optimizer", "adam") == "adam":
         ck["optimizer"] = adam_state_dict(module, engine.store, engine.host_step, lr)
     return ck
 
