@@ -197,6 +197,10 @@ int mnb_counter_inc(long long* counter, void* stream);
 
 /* ---- layout helpers --------------------------------------------------------------------------------- */
 int mnb_nhwc_to_nchw_f32(const void* x, float* y, int N, int H, int W, int C, int dtype, void* stream);
+/* input pipeline: y[n,c,h,w] = (x[n,h,w,c] / 255 - mean[c]) / std[c], uint8 HWC -> fp32 NCHW, i.e. transforms.ToTensor +
+ * transforms.Normalize (utils/datasets.py:460-462) with FineTuneModelPool.mean / .std (classifiers.py:91-92) */
+int mnb_u8hwc_to_nchw_f32(const unsigned char* x, const float* mean, const float* std, float* y, int N, int H, int W,
+                          int C, void* stream);
 int mnb_nchw_f32_to_nhwc(const float* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
 
 #ifdef __cplusplus

@@ -608,6 +608,22 @@ __global__ void nchw_to_nhwc_k(const float* __restrict__ x, T* __restrict__ y, i
     }
 }
 
+// transforms.ToTensor() + transforms.Normalize(mean, std) (src/utils/datasets.py:460-462) on the device: uint8 HWC in,
+// the fp32 NCHW tensor train.py:427 hands to the model out -- the host then ships 1 byte per value instead of 4
+__global__ void u8hwc_to_nchw_norm_k(const unsigned char* __restrict__ x, const float* __restrict__ mean,
+                                     const float* __restrict__ stdv, float* __restrict__ y, int N, int HW, int C) {
+    const long long total = (long long)N * HW * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        // i runs over the OUTPUT (coalesced fp32 stores; the byte gathers hit in L1)
+        const int p = (int)(i % HW);
+        const int c = (int)((i / HW) % C);
+        const long long n = i / ((long long)HW * C);
+        const float v = (float)x[(n * HW + p) * C + c] / 255.f;
+        y[i] = (v - mean[c]) / stdv[c];
+    }
+}
+
 static inline unsigned flat_grid(long long nvec, int ctas_per_sm = 8) {
     long long b = cdiv(nvec, 256);
     long long cap = (long long)num_sms() * ctas_per_sm;
@@ -869,6 +885,15 @@ __global__ void counter_inc_k(long long* c) { *c += 1; }
 int mnb_counter_inc(long long* counter, void* stream) {
     counter_inc_k<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
     MNB_LAUNCH_CHECK("counter_inc");
+    return 0;
+}
+
+int mnb_u8hwc_to_nchw_f32(const unsigned char* x, const float* mean, const float* stdv, float* y, int N, int H, int W,
+                          int C, void* stream) {
+    const long long total = (long long)N * H * W * C;
+    MNB_REQUIRE(total > 0 && x && mean && stdv && y, "u8hwc_to_nchw: empty or NULL argument");
+    u8hwc_to_nchw_norm_k<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(x, mean, stdv, y, N, H * W, C);
+    MNB_LAUNCH_CHECK("u8hwc_to_nchw");
     return 0;
 }
 

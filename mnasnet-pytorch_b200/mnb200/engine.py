@@ -810,6 +810,29 @@ class Engine:
         self.optimizer_step(lr, betas, eps, gscale)
         return plan.loss
 
+    def normalize_u8(self, x_u8: torch.Tensor) -> torch.Tensor:
+        """uint8 N x H x W x C image batch (host or device) -> the normalised fp32 N x C x H x W device tensor the step
+        consumes: ToTensor + Normalize(module.mean, module.std) on the device (utils/datasets.py:460-462), so the
+        host-to-device copy carries one byte per value.  The result lives in a per-shape buffer."""
+        if x_u8.dtype != torch.uint8 or x_u8.dim() != 4:
+            raise ValueError("expected a uint8 N x H x W x C tensor")
+        x_u8 = x_u8.to(self.device, non_blocking=True).contiguous()
+        N, H, W, C = x_u8.shape
+        if getattr(self, "_norm", None) is None:
+            mean = getattr(self.module, "mean", (0.0,) * C)
+            std = getattr(self.module, "std", (1.0,) * C)
+            self._norm = (torch.tensor(mean, device=self.device, dtype=torch.float32),
+                          torch.tensor(std, device=self.device, dtype=torch.float32), {})
+        mean, std, bufs = self._norm
+        if mean.numel() != C:
+            raise ValueError(f"{C} channels, but module.mean has {mean.numel()}")
+        y = bufs.get((N, H, W))
+        if y is None:
+            y = bufs[(N, H, W)] = torch.empty((N, C, H, W), device=self.device, dtype=torch.float32)
+        check(lib.mnb_u8hwc_to_nchw_f32(x_u8.data_ptr(), mean.data_ptr(), std.data_ptr(), y.data_ptr(), N, H, W, C,
+                                        torch.cuda.current_stream().cuda_stream), "u8hwc_to_nchw")
+        return y
+
     def optimizer_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, lr_on_device=False):
         """`optimizer.step()` of the optimizer selected by `Engine.optimizer` (train.py:218-231: 'adam' | 'rmsprop' |
         'sgd', all with torch's defaults) over the flat parameter / gradient buffers."""

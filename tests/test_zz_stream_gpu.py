@@ -260,3 +260,21 @@ def test_other_optimizers_match_torch(opt_name):
     assert math.isfinite(l1) and not torch.equal(before, eng.store.flat)
     if opt_name == "sgd":
         torch.testing.assert_close(eng.store.flat, before - 1e-3 * eng.store.grad, rtol=1e-6, atol=1e-7)
+
+
+def test_uint8_input_pipeline_matches_totensor_normalize():
+    """uint8 HWC batch -> ToTensor + Normalize(mean, std) on the device, bit-for-bit the torch result."""
+    from mnb200 import engine
+    m = _build("fp32")
+    eng = engine.engine_for(m)
+    g = torch.Generator().manual_seed(0)
+    x8 = torch.randint(0, 256, (3, 64, 96, 3), generator=g, dtype=torch.uint8)
+    y = eng.normalize_u8(x8)
+    torch.cuda.synchronize()
+    mean = torch.tensor(m.mean)[None, :, None, None]
+    std = torch.tensor(m.std)[None, :, None, None]
+    ref = (x8.permute(0, 3, 1, 2).float().div(255) - mean) / std
+    assert y.shape == (3, 3, 64, 96) and y.dtype == torch.float32
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-6, atol=1e-6)
+    out = m(y)                                      # feeds the step like any fp32 NCHW batch
+    assert out.shape == (3, 1000) and torch.isfinite(out).all()
