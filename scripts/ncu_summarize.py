@@ -3,6 +3,8 @@ bench.py (with --dump-ops) into per-kernel-class shares and DRAM traffic -> prof
 compact launch list profiles/r1_ncu_launch_list.csv."""
 import collections, csv, json, sys
 src, opsf = sys.argv[1], sys.argv[2]
+tag = sys.argv[3] if len(sys.argv) > 3 else 'r1'            # round tag of the output file names
+outdir = sys.argv[4] if len(sys.argv) > 4 else 'profiles'
 rows = [r for r in csv.reader(open(src)) if len(r) > 10]
 hdr = rows[0]
 ix = {k: hdr.index(k) for k in ('Kernel Name', 'Metric Name', 'Metric Value', 'ID', 'Metric Unit', 'Grid Size', 'Block Size')}
@@ -39,8 +41,8 @@ for k, c in sorted(cls.items(), key=lambda kv: -kv[1]['us']):
     out['classes'][k] = {'sass_kernels': sorted(c['kernels']), 'launches_per_step': c['launches'],
                          'us_per_step': round(c['us'], 1), 'share': round(c['us'] / tot, 4),
                          'dram_GB_per_step': round(c['dram'] / 1e9, 3)}
-json.dump(out, open('profiles/r1_ncu_step_summary.json', 'w'), indent=1)
-with open('profiles/r1_ncu_launch_list.csv', 'w') as f:
+json.dump(out, open(f'{outdir}/{tag}_ncu_step_summary.json', 'w'), indent=1)
+with open(f'{outdir}/{tag}_ncu_launch_list.csv', 'w') as f:
     f.write('id,kernel,grid,block,gpu__time_duration_us,dram_read_bytes,dram_write_bytes\n')
     for i, l in enumerate(step):
         f.write(f'{i},"{l["name"]}","{l["grid"]}","{l["block"]}",{l["us"]:.2f},{l.get("dram__bytes_read.sum",0):.0f},{l.get("dram__bytes_write.sum",0):.0f}\n')
