@@ -360,6 +360,7 @@ def main():
                 "config": {"workload": WORKLOAD if (N, S) == (256, 224) else f"MnasNet {S}x{S} batch {N}/GPU",
                            "global_batch": N * world, "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-3",
                            "dropout": "active", "cuda_graph": bool(use_graph), "gemm_impl": args.gemm,
+                           "kernel_options": _kernel_options(),
                            "l2": "no flush needed: each step streams a 154 MB input batch (2 alternating "
                                  "buffers) and ~6 GB of activations, both >> 126 MB L2"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -367,6 +368,15 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _kernel_options():
+    """Which kernel families `impl` auto selects (mnb_get_option): recorded with every bench line."""
+    try:
+        from mnb200 import _lib
+        return {n: _lib.get_option(n) for n in ("pw_stream", "stem_mma", "dw_stream", "dw_stream_pd")}
+    except Exception as e:      # never lose a measurement over a label
+        return {"error": str(e)}
 
 
 if __name__ == "__main__":
