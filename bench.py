@@ -374,7 +374,7 @@ def _kernel_options():
     """Which kernel families `impl` auto selects (mnb_get_option): recorded with every bench line."""
     try:
         from mnb200 import _lib
-        return {n: _lib.get_option(n) for n in ("pw_stream", "stem_mma", "dw_stream", "dw_stream_pd")}
+        return {n: _lib.get_option(n) for n in ("pw_stream", "stem_mma", "dw_stream", "dw_stream_pd", "dw_stream_tw8")}
     except Exception as e:      # never lose a measurement over a label
         return {"error": str(e)}
 

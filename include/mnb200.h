@@ -47,6 +47,8 @@ int mnb_version(void);
  *                            (forward / backward-data on maps of <= 7 rows and of the 5x5 layers on >= 56 rows)
  *   "dw_stream_pd" (default 1)  input rows the row-stream kernels keep in flight ahead of the one they consume (1..3;
  *                            2 and 3 are untimed experiments: more memory-level parallelism, more registers)
+ *   "dw_stream_tw8" (default 0) 3x3 row-stream forward / backward-data with 8 instead of 4 output columns per lane
+ *                            (fewer halo loads and per-row overheads per output, more registers; untimed experiment)
  * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current value or MNB_ERR_ARG. */
 int mnb_set_option(const char* name, int value);
 int mnb_get_option(const char* name);

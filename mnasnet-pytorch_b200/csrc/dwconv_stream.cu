@@ -534,6 +534,7 @@ int dw_fwd_stream(const void* x, const float* s, const float* t, const float* w,
     DwSP p = {};
     p.x = (const bf16*)x; p.in_scale = s; p.in_shift = t; p.w = w; p.bias = bias; p.out = (bf16*)z; p.stats = stats;
     p.N = N; p.H = H; p.W = W; p.C = C;
+    if (k == 3 && option_get(OPT_DW_STREAM_TW8)) return dws_launch<3, 8, DWS_FWD, 3>(p, st, "dw_fwd(stream, 8 columns)");
     if (k == 3) return dws_launch<3, 4, DWS_FWD, 4>(p, st, "dw_fwd(stream)");
     return dws_launch<5, 4, DWS_FWD, 3>(p, st, "dw_fwd(stream)");
 }
@@ -542,6 +543,7 @@ int dw_dgrad_stream(const void* dz, const float* w, void* dx, int N, int H, int 
     DwSP p = {};
     p.x = (const bf16*)dz; p.w = w; p.out = (bf16*)dx;
     p.N = N; p.H = H; p.W = W; p.C = C;
+    if (k == 3 && option_get(OPT_DW_STREAM_TW8)) return dws_launch<3, 8, DWS_DGRAD, 3>(p, st, "dw_dgrad(stream, 8 columns)");
     if (k == 3) return dws_launch<3, 4, DWS_DGRAD, 4>(p, st, "dw_dgrad(stream)");
     return dws_launch<5, 4, DWS_DGRAD, 3>(p, st, "dw_dgrad(stream)");
 }
@@ -615,7 +617,7 @@ static int emul_run_pd(DwSP p, int total_warps) {
 }  // namespace mnb
 
 namespace mnb {
-static int g_emul_pd = 1;
+static int g_emul_pd = 1, g_emul_tw8 = 0;
 template <int K, int TW, int MODE>
 static int emul_run(const DwSP& p, int total_warps) {
     if (g_emul_pd >= 3) return emul_run_pd<K, TW, MODE, 3>(p, total_warps);
@@ -624,6 +626,7 @@ static int emul_run(const DwSP& p, int total_warps) {
 }
 }  // namespace mnb
 extern "C" void mnb_emul_dw_stream_set_pd(int pd) { mnb::g_emul_pd = pd; }
+extern "C" void mnb_emul_dw_stream_set_tw8(int on) { mnb::g_emul_tw8 = on; }
 
 // all pointers are HOST pointers; mode 0 fwd / 1 dgrad / 2 wgrad; geometry[6] returns PL, G, NB, HS, nws, nhs
 extern "C" int mnb_emul_dw_stream(int mode, const void* x, const float* s, const float* t, const float* w,
@@ -635,11 +638,13 @@ extern "C" int mnb_emul_dw_stream(int mode, const void* x, const float* s, const
     p.out = (bf16*)out; p.dw = dw; p.stats = stats; p.N = N; p.H = H; p.W = W; p.C = C;
     if (geometry) {
         DwSP q = p;
-        const int tw = (mode == 2 && k == 5) ? 2 : 4;
+        const int tw = (mode == 2 && k == 5) ? 2 : ((k == 3 && mode != 2 && g_emul_tw8) ? 8 : 4);
         if (!dws_geometry(q, tw, total_warps)) return MNB_ERR_UNSUPPORTED;
         geometry[0] = q.PL; geometry[1] = q.G; geometry[2] = q.NB; geometry[3] = q.HS; geometry[4] = q.nws; geometry[5] = q.nhs;
     }
     if (k == 3) {
+        if (mode == 0 && g_emul_tw8) return emul_run<3, 8, DWS_FWD>(p, total_warps);
+        if (mode == 1 && g_emul_tw8) return emul_run<3, 8, DWS_DGRAD>(p, total_warps);
         if (mode == 0) return emul_run<3, 4, DWS_FWD>(p, total_warps);
         if (mode == 1) return emul_run<3, 4, DWS_DGRAD>(p, total_warps);
         return emul_run<3, 4, DWS_WGRAD>(p, total_warps);

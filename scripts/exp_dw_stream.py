@@ -80,9 +80,13 @@ def layer_case(N, H, C, k):
     sh = (torch.randn(C, device=dev, generator=g) * 0.3).float()
     out = {"shape": f"{N}x{H}x{W}x{C} k{k}", "bytes_fwd": 2 * x.numel() * 2}
     res = {}
-    for tag, opt, pd in (("tile", 0, 1), ("stream", 1, 1), ("stream_pd2", 1, 2), ("stream_pd3", 1, 3)):
+    for tag, opt, pd, tw8 in (("tile", 0, 1, 0), ("stream", 1, 1, 0), ("stream_pd2", 1, 2, 0), ("stream_pd3", 1, 3, 0),
+                              ("stream_tw8", 1, 1, 1), ("stream_tw8_pd3", 1, 3, 1)):
+        if tw8 and k != 3:
+            continue
         L.set_option("dw_stream", opt)
         L.set_option("dw_stream_pd", pd)
+        L.set_option("dw_stream_tw8", tw8)
         z = torch.full_like(x, float("nan"))
         st = torch.zeros(2 * C, device=dev, dtype=torch.float64)
         dx = torch.full_like(x, float("nan"))
@@ -104,9 +108,10 @@ def layer_case(N, H, C, k):
         out[f"wgrad_us_{tag}"] = round(timeit(f_wg), 1)
     L.set_option("dw_stream", 0)
     L.set_option("dw_stream_pd", 1)
+    L.set_option("dw_stream_tw8", 0)
     z0, st0, dx0, dw0 = res["tile"]
     ok = True
-    for tag in ("stream", "stream_pd2", "stream_pd3"):
+    for tag in [t for t in res if t != "tile"]:
         z1, st1, dx1, dw1 = res[tag]
         nan = int(torch.isnan(z1.float()).sum().item() + torch.isnan(dx1.float()).sum().item())
         rels = (relerr(z1.float(), z0.float()), relerr(st1, st0), relerr(dx1.float(), dx0.float()), relerr(dw1, dw0))
@@ -122,9 +127,10 @@ def net_case(n_big, steps):
     xb = torch.randn(n_big, 3, 224, 224, device=dev)
     tb = torch.randint(0, 1000, (n_big,), device=dev)
     big = {}
-    for opt, pd in ((0, 1), (1, 1), (2, 1), (1, 3), (2, 3)):
+    for opt, pd, tw8 in ((0, 1, 0), (1, 1, 0), (2, 1, 0), (1, 3, 0), (2, 3, 0), (1, 3, 1)):
         L.set_option("dw_stream", opt)              # graphs captured now keep the kernels selected now
         L.set_option("dw_stream_pd", pd)
+        L.set_option("dw_stream_tw8", tw8)
         torch.manual_seed(42)
         m = FineTuneModelPool(load_model('mnasnet'), 'mnasnet', 1000, '512')
         engine.configure(m, dtype="bf16")
@@ -141,7 +147,7 @@ def net_case(n_big, steps):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        tag = ("tile", "stream", "auto")[opt] + (f"_pd{pd}" if pd > 1 else "")
+        tag = ("tile", "stream", "auto")[opt] + (f"_pd{pd}" if pd > 1 else "") + ("_tw8" if tw8 else "")
         big[f"ms_per_step_{tag}"] = round(ms, 3)
         big[f"img_per_s_{tag}"] = round(n_big / ms * 1e3, 1)
         big[f"loss_first_{tag}"] = first
@@ -150,6 +156,7 @@ def net_case(n_big, steps):
         torch.cuda.empty_cache()
     L.set_option("dw_stream", 0)
     L.set_option("dw_stream_pd", 1)
+    L.set_option("dw_stream_tw8", 0)
     item("net_big", **big)
 
 

@@ -42,6 +42,9 @@ def emul():
     fn.set_pd = lib.mnb_emul_dw_stream_set_pd
     fn.set_pd.argtypes = [ctypes.c_int]
     fn.set_pd.restype = None
+    fn.set_tw8 = lib.mnb_emul_dw_stream_set_tw8
+    fn.set_tw8.argtypes = [ctypes.c_int]
+    fn.set_tw8.restype = None
     return fn
 
 
@@ -75,11 +78,14 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("pd", [1, 2, 3])
+@pytest.mark.parametrize("pd,tw8", [(1, 0), (2, 0), (3, 0), (1, 1), (3, 1)])
 @pytest.mark.parametrize("case", CASES)
-def test_lane_program_matches_torch(emul, case, pd):
+def test_lane_program_matches_torch(emul, case, pd, tw8):
     N, H, W, C, k, xform, warps = case
+    if tw8 and k != 3:
+        pytest.skip("8-column strips exist for 3x3 only")
     emul.set_pd(pd)                                    # rows of prefetch kept in flight (option "dw_stream_pd")
+    emul.set_tw8(tw8)                                  # 8 output columns per lane (option "dw_stream_tw8")
     g = torch.Generator().manual_seed(N * 100 + H + C)
     x = torch.randn(N, H, W, C, generator=g).to(torch.bfloat16)
     w = (torch.randn(C, 1, k, k, generator=g) / k).float()
@@ -94,7 +100,7 @@ def test_lane_program_matches_torch(emul, case, pd):
     rc = emul(0, P(x), P(s), P(t), P(w), P(b), None, P(z), None, P(stats), N, H, W, C, k, warps, ctypes.addressof(geo))
     assert rc == 0
     PL, G, NB, HS, nws, nhs = list(geo)
-    assert PL * G <= 32 and PL * NB * 2 == C and nhs * HS >= H and nws * 4 * G >= W
+    assert PL * G <= 32 and PL * NB * 2 == C and nhs * HS >= H and nws * (8 if tw8 else 4) * G >= W
     xa = x.float().permute(0, 3, 1, 2).double()
     a = torch.relu(xa * s.double()[None, :, None, None] + t.double()[None, :, None, None]) if xform else xa
     a_ = a.clone().requires_grad_(True)

@@ -165,7 +165,7 @@ def test_kernel_selection_options():
     _lib.set_option("dw_stream", 2)
     assert _lib.get_option("dw_stream") == 2
     _lib.set_option("dw_stream", 0)
-    assert _lib.get_option("dw_stream_pd") == 1
+    assert _lib.get_option("dw_stream_pd") == 1 and _lib.get_option("dw_stream_tw8") == 0
     with pytest.raises(_lib.MnbError):
         _lib.set_option("no_such_option", 1)
 
