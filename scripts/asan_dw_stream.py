@@ -6,7 +6,7 @@ the lane program (padding, edge strips, prefetch offsets) aborts.  Usage:
     nvcc -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 -Xcompiler -fPIC,-fsanitize=address \
          -DMNB_DW_STREAM_EMUL -shared mnasnet-pytorch_b200/csrc/dwconv_stream.cu -o gpurun_out/asan/libdw_stream_emul.so
     LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 python scripts/asan_dw_stream.py gpurun_out/asan/libdw_stream_emul.so
-Last run (round 1): 17 shapes x prefetch depth 1/2/3 x fwd/dgrad/wgrad, clean."""
+Last run (round 1): 17 shapes x (prefetch depth 1/2/3, 4- and 8-column strips) x fwd/dgrad/wgrad, clean."""
 import ctypes
 import sys
 
@@ -15,6 +15,7 @@ fn = lib.mnb_emul_dw_stream
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 9 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
 lib.mnb_emul_dw_stream_set_pd.argtypes = [ctypes.c_int]
+lib.mnb_emul_dw_stream_set_tw8.argtypes = [ctypes.c_int]
 libc = ctypes.CDLL("libc.so.6")
 libc.malloc.restype = ctypes.c_void_p
 libc.malloc.argtypes = [ctypes.c_size_t]
@@ -30,8 +31,9 @@ CASES = [(2, 12, 10, 32, 3, 8), (1, 9, 11, 72, 5, 12), (2, 7, 7, 48, 3, 6), (1, 
          (1, 33, 17, 16, 3, 40), (3, 14, 14, 64, 5, 5), (1, 5, 6, 1152, 3, 36), (2, 2, 2, 1152, 3, 592),
          (2, 4, 4, 576, 5, 444), (1, 1, 1, 240, 5, 444), (2, 64, 48, 72, 5, 444), (1, 9, 70, 32, 3, 16),
          (2, 20, 100, 48, 5, 24), (1, 12, 66, 16, 3, 10), (1, 3, 200, 16, 5, 7), (2, 57, 3, 24, 3, 9)]
-for pd in (1, 2, 3):
+for pd, tw8 in ((1, 0), (2, 0), (3, 0), (1, 1), (3, 1)):
     lib.mnb_emul_dw_stream_set_pd(pd)
+    lib.mnb_emul_dw_stream_set_tw8(tw8)        # 8-column strips (3x3 forward / backward-data)
     for (N, H, W, C, k, warps) in CASES:
         n = N * H * W * C
         x, dz, out = buf(2 * n), buf(2 * n), buf(2 * n)
@@ -43,5 +45,5 @@ for pd in (1, 2, 3):
             assert rc == 0, (rc, N, H, W, C, k)
         for p in (x, dz, out, s, t, b, w, dw, st):
             libc.free(p)
-        print("ok", pd, (N, H, W, C, k, warps), flush=True)
+        print("ok", pd, tw8, (N, H, W, C, k, warps), flush=True)
 print("ASAN CLEAN")
