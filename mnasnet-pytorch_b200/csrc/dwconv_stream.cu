@@ -213,16 +213,18 @@ MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, 
                     for (int j = 0; j < NI; ++j) raw[d][j] = raw[d + 1][j];
                 load_row(r + PD, off_next, raw[PD - 1]);
                 off_next += rs;
+                // This input row feeds output row o = r + P - kh through kernel row kh; slot (o - h0) % K = (u - kh) % K is
+                // static after unrolling.  Kernel row 0 is always the FIRST contribution to its output row, so it
+                // overwrites the slot: no zeroing, and rows outside [h0, h1) need no test -- what they leave in a slot
+                // is overwritten before the slot's next real row starts, or never stored.
 #pragma unroll
                 for (int kh = 0; kh < K; ++kh) {
-                    const int o = r + P - kh;          // output row fed by this input row through kernel row kh
-                    if (o >= h0 && o < h1) {
-                        const int slot = (u - kh + 2 * K) % K;        // (o - h0) % K, static after unrolling
+                    const int slot = (u - kh + 2 * K) % K;
 #pragma unroll
-                        for (int tc = 0; tc < TW; ++tc)
+                    for (int tc = 0; tc < TW; ++tc)
 #pragma unroll
-                            for (int kw = 0; kw < K; ++kw) acc[slot][tc] = f2_fma(in[tc + kw], wr[kh][kw], acc[slot][tc]);
-                    }
+                        for (int kw = 0; kw < K; ++kw)
+                            acc[slot][tc] = f2_fma(in[tc + kw], wr[kh][kw], (kh == 0 && kw == 0) ? zero2 : acc[slot][tc]);
                 }
                 const int od = r - P;                  // output row completed by this input row (kernel row K-1)
                 if (od >= h0 && od < h1) {
@@ -231,7 +233,6 @@ MNB_HD void dws_conv_task(const DwSP& p, int n, int h0, int h1, int c0, int ch, 
                     for (int tc = 0; tc < TW; ++tc) {
                         float v0, v1;
                         f2_get(acc[slot][tc], v0, v1);
-                        acc[slot][tc] = zero2;
                         if (!EDGE || ((omask >> tc) & 1u)) {
                             const uint32_t pk = pack2_rn(v0 + b0, v1 + b1);
                             *reinterpret_cast<uint32_t*>(p.out + (ooff + jC[tc])) = pk;
@@ -349,16 +350,15 @@ MNB_HD void dws_wgrad_task(const DwSP& p, int n, int h0, int h1, int c0, int ch,
                 }
                 load_rows(r + PD, xoff_next, goff_next, rawx[PD - 1], rawg[PD - 1]);
                 xoff_next += rs; goff_next += rs;
+                // dz row o = r + P - kh pairs with this input row through kernel row kh; the ring holds zeros for rows
+                // outside [h0, h1) (initial state / masked loads), so no range test is needed
 #pragma unroll
                 for (int kh = 0; kh < K; ++kh) {
-                    const int o = r + P - kh;          // dz row paired with this input row through kernel row kh
-                    if (o >= h0 && o < h1) {
-                        const int slot = (u - kh + 2 * K) % K;
+                    const int slot = (u - kh + 2 * K) % K;
 #pragma unroll
-                        for (int tc = 0; tc < TW; ++tc)
+                    for (int tc = 0; tc < TW; ++tc)
 #pragma unroll
-                            for (int kw = 0; kw < K; ++kw) wg[kh][kw] = f2_fma(in[tc + kw], g[slot][tc], wg[kh][kw]);
-                    }
+                        for (int kw = 0; kw < K; ++kw) wg[kh][kw] = f2_fma(in[tc + kw], g[slot][tc], wg[kh][kw]);
                 }
             }
         }
