@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+from torch import nn
 
 
 def bucket_schedule(buckets, offsets_last_write):
@@ -112,3 +113,27 @@ def broadcast_parameters(engine, src=0, group=None):
     dist.broadcast(engine.store.flat, src=src, group=group)
     dist.broadcast(engine.store.fbuf, src=src, group=group)
     dist.broadcast(engine.store.ibuf, src=src, group=group)
+
+
+class DataParallel(nn.Module):
+    """``model = torch.nn.DataParallel(model)`` (src/train.py:202) for the process-per-GPU layout: the wrapper the
+    training script keeps calling -- ``model(input)``, ``model.module.parameters()`` (:210-212), ``model.state_dict()``
+    with ``module.``-prefixed keys (:383), ``load_state_dict`` (:242), ``train()/eval()`` -- while every process owns
+    one replica and one batch shard.  With torch.distributed initialised (torchrun) the replicas are synchronised once
+    from rank 0 and a GradSync is attached to the module's engine, so ``loss.backward()`` all-reduces (averages) the
+    gradients bucket by bucket while backward runs; without it (single GPU) this is a transparent wrapper.
+    ``device_ids`` / ``output_device`` / ``dim`` are accepted for signature compatibility and ignored."""
+
+    def __init__(self, module: nn.Module, device_ids=None, output_device=None, dim=0, group=None, overlap=True):
+        super().__init__()
+        from .engine import engine_for
+        self.module = module
+        self.device_ids, self.output_device, self.dim = device_ids, output_device, dim
+        self.sync = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            eng = engine_for(module)
+            broadcast_parameters(eng, 0, group)
+            self.sync = GradSync(eng, group, overlap)
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)

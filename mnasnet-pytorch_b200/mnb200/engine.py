@@ -99,14 +99,38 @@ class ParamStore:
         self.v = None
 
     def valid(self):
-        for p in (self.params[0], self.params[-1]):
-            o, _ = self.offsets[id(p)]
-            if p.data_ptr() != self.flat.data_ptr() + 4 * o:
+        """Every parameter and buffer still aliases its slot of the flat stores (a sub-module lowered on its own, or
+        model.to(), re-homes them: the engine then rebuilds, see Engine._check_store)."""
+        base = self.flat.data_ptr()
+        for p in self.params:
+            if p.data_ptr() != base + 4 * self.offsets[id(p)][0]:
                 return False
-        for lst, buf in ((self._fb, self.fbuf), (self._ib, self.ibuf)):
-            if lst and lst[0].data_ptr() != buf.data_ptr():
-                return False
+        for lst, buf, es in ((self._fb, self.fbuf, 4), (self._ib, self.ibuf, 8)):
+            o = buf.data_ptr()
+            for b in lst:
+                if b.data_ptr() != o:
+                    return False
+                o += es * b.numel()
         return True
+
+    def trainable_ranges(self):
+        """Contiguous [lo, hi) slices of the flat buffers whose parameters have requires_grad (the reference builds
+        its optimizer from filter(lambda p: p.requires_grad, ...), src/train.py:219): after
+        FineTuneModelPool.freeze() (classifiers.py:94-99) this is the classifier slice alone."""
+        out = []
+        for p in self.params:
+            if not p.requires_grad:
+                continue
+            o, n = self.offsets[id(p)]
+            hi = o + (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            if out and out[-1][1] == o:
+                out[-1][1] = hi
+            else:
+                out.append([o, hi])
+        return [tuple(r) for r in out]
+
+    def trainable_sig(self):
+        return tuple(p.requires_grad for p in self.params)
 
     def gptr(self, p):
         return self.grad.data_ptr() + 4 * self.offsets[id(p)][0]
@@ -198,6 +222,8 @@ class Plan:
             ref = Ref(None, N, H, W, 3, nchw=True)
             ref = self._emit(mod.features, ref)
             self._emit_head(mod, ref)
+            if self.dropout_masks:
+                self._op(self.fwd, "mnb_counter_inc", eng.dev_fwd, label="fwd_counter")
         else:
             cin = eng.in_channels
             # standalone sub-module: convert the NCHW fp32 input to NHWC once, run, convert back
@@ -416,10 +442,34 @@ class Plan:
                 ops.append(_EventOp("wait", ev, 0))
             return b
         net = getattr(eng.module, "_mnb", None) == "net"
+
+        def rg(p):
+            return p is not None and p.requires_grad
+
+        def Gp(p):                         # gradient slot, or NULL for a frozen parameter (freeze(), classifiers.py:94)
+            return _G(p) if rg(p) else None
+        # frozen parameters get no gradient and backward stops below the first (in forward order) ConvBlock that
+        # still has a trainable parameter -- what autograd does for requires_grad=False leaves (train.py:219)
+        first_live = None
+        for ti, entry in enumerate(self.tape):
+            if entry[0] == "conv":
+                cbk = entry[1].cb
+                if rg(cbk.conv.weight) or rg(cbk.conv.bias) or rg(cbk.bn.weight) or rg(cbk.bn.bias):
+                    first_live = ti
+                    break
+        sub_needs_dx = not net             # a stand-alone sub-module returns the input gradient
+        if first_live is None and not sub_needs_dx:
+            first_live = len(self.tape)    # nothing trainable in the features: backward ends at the head
+        if sub_needs_dx:
+            first_live = -1                # walk the whole tape and keep the first conv's data gradient
+        self.bwd_stop = first_live
         if net:
             # head backward
             g = self.dlogits
+            head_live = [rg(r["lin"].weight) or rg(r["lin"].bias) for r in self.head]
             for i in range(len(self.head) - 1, -1, -1):
+                if first_live >= len(self.tape) and not any(head_live[:i + 1]):
+                    break                  # nothing trainable below this layer
                 r = self.head[i]
                 lin = r["lin"]
                 maskp = _MaskPtr(self, r["mask"]) if r["mask"] is not None else None
@@ -428,25 +478,33 @@ class Plan:
                 relu_ref = r["x"] if (i > 0 and self.head[i - 1]["relu"]) else None
                 if r["tc"]:
                     self._op(ops, "mnb_fc_prep_bf16", g, None, 1.0, r["dyb"], self.N * r["O"])
-                    self._op(ops, "mnb_conv_wgrad", r["xb"], None, None, r["dyb"], _G(lin.weight), self.N, 1, 1,
-                             r["K"], r["O"], 1, 1, 0, _lib.MNB_BF16, _lib.LAYOUT_NHWC, 0, label="fc_wgrad(tcgen05)")
-                    self._op(ops, "mnb_fc_bias_grad", g, _G(lin.bias), self.N, r["O"])
+                    if rg(lin.weight):
+                        self._op(ops, "mnb_conv_wgrad", r["xb"], None, None, r["dyb"], _G(lin.weight), self.N, 1, 1,
+                                 r["K"], r["O"], 1, 1, 0, _lib.MNB_BF16, _lib.LAYOUT_NHWC, 0,
+                                 label="fc_wgrad(tcgen05)")
+                    if rg(lin.bias):
+                        self._op(ops, "mnb_fc_bias_grad", g, _G(lin.bias), self.N, r["O"])
                     self._op(ops, "mnb_fc_dgrad_tc", r["dyb"], lin.weight, r["pd"], dx, self.N, r["K"], r["O"],
                              label="fc_dgrad(tcgen05)")
                     self._op(ops, "mnb_fc_gate", dx, maskp, ms, relu_ref, self.N * r["K"])
                 else:
-                    self._op(ops, "mnb_fc_wgrad", r["x"], maskp, ms, g, _G(lin.weight), _G(lin.bias), self.N,
-                             r["K"], r["O"])
+                    if rg(lin.weight) or rg(lin.bias):
+                        if not (rg(lin.weight) and rg(lin.bias)):
+                            raise NotImplementedError("mnb200: freeze a Linear's weight and bias together")
+                        self._op(ops, "mnb_fc_wgrad", r["x"], maskp, ms, g, _G(lin.weight), _G(lin.bias), self.N,
+                                 r["K"], r["O"])
                     self._op(ops, "mnb_fc_dgrad", g, lin.weight, maskp, ms, relu_ref, dx, self.N, r["K"], r["O"])
                 g = dx
-            gbuf = take()
-            hi = self.head_in
-            self._op(ops, "mnb_gap_bwd", g, gbuf, self.N, hi.H * hi.W, hi.C, self.code)
+            gbuf = None
+            if first_live < len(self.tape):
+                gbuf = take()
+                hi = self.head_in
+                self._op(ops, "mnb_gap_bwd", g, gbuf, self.N, hi.H * hi.W, hi.C, self.code)
         else:
             gbuf = take()
             self.sub_dout = gbuf          # filled from the NCHW grad_output at run time
         held = []                          # stack of residual-skip gradients
-        for idx in range(len(self.tape) - 1, -1, -1):
+        for idx in range(len(self.tape) - 1, max(first_live, 0) - 1, -1):
             entry = self.tape[idx]
             tag = entry[0]
             if tag == "res_end":
@@ -467,7 +525,7 @@ class Plan:
                     self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
                              nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
                 self._op(ops, "mnb_bn_bwd_apply_fused", gbuf, a.z, a.scale, a.shift, a.sums, a.mean, a.invstd,
-                         _G(bn.weight), _G(bn.bias), _G(conv.bias), dz, M, C, a.m, self.code,
+                         Gp(bn.weight), Gp(bn.bias), Gp(conv.bias), dz, M, C, a.m, self.code,
                          nbytes=3 * a.out_bytes, label="bn_bwd_apply")
                 in_held = any(gbuf is h for h in held)
                 if not in_held:
@@ -475,24 +533,25 @@ class Plan:
                 r = a.inp
                 x_t = r.t if not r.nchw else _InputPtr(self)
                 layout = _lib.LAYOUT_NCHW_F32 if r.nchw else _lib.LAYOUT_NHWC
-                if side:                   # fork: the side stream may start once dZ is complete
+                wg = rg(conv.weight)
+                if side and wg:            # fork: the side stream may start once dZ is complete
                     ev_dz = self._new_event()
                     ops.append(_EventOp("record", ev_dz, 0))
                     ops.append(_EventOp("wait", ev_dz, 1))
-                if a.kind == "dense":
+                if wg and a.kind == "dense":
                     self._op(ops, "mnb_conv_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W,
                              r.C, C, a.k, a.stride, a.pad, self.code, layout, eng.impl,
                              nbytes=a.in_bytes + a.out_bytes, label=a.label + "_wgrad")
-                else:
+                elif wg:
                     self._op(ops, "mnb_dw_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W, r.C,
                              a.k, self.code, nbytes=a.in_bytes + a.out_bytes, label=a.label + "_wgrad")
-                if side:
+                if side and wg:
                     ops[-1].stream_id = 1
                     ev_w = self._new_event()
                     ops.append(_EventOp("record", ev_w, 1))
                     pending[id(dz)] = ev_w
                     self.side_last = ev_w
-                if a.need_dgrad:
+                if a.need_dgrad and idx > first_live:
                     dx = take()
                     # the first conv of a residual block adds the skip gradient (dY) into its dgrad output
                     add = None
@@ -697,14 +756,16 @@ class _DropoutOp:
         if not plan.dropout_active or plan.masks_injected:
             return
         eng = plan.eng
+        # counter-based RNG keyed by (seed, per-forward counter, layer): a fresh mask per training forward
+        # (nn.Dropout draws one per call, classifiers.py:82,85), independent of the optimizer step
         check(lib.mnb_dropout_mask(self.mask.data_ptr(), self.n, self.p, eng.seed,
-                                   (self.idx + 1) << 40, eng.dev_step.data_ptr(), stream), self.name)
+                                   (self.idx + 1) << 40, eng.dev_fwd.data_ptr(), stream), self.name)
 
 
 class Engine:
     """Owns the flat parameter store and the per-shape plans of one lowered module."""
 
-    def __init__(self, module: nn.Module, dtype: str = "bf16", impl: str = "auto", device=None, seed: int = 0):
+    def __init__(self, module: nn.Module, dtype: str = "bf16", impl: str = "auto", device=None, seed=None):
         _require_cuda()
         if dtype not in DTYPES:
             raise ValueError(f"dtype must be one of {list(DTYPES)}")
@@ -714,10 +775,12 @@ class Engine:
         self.in_channels = _first_conv(module).in_channels
         self.store = ParamStore(module, self.device)
         self.plans = {}
-        self.seed = int(seed)
-        self.dev_step = torch.zeros(1, device=self.device, dtype=torch.long)   # optimizer / RNG step counter
+        # dropout stream: torch's seed (torch.manual_seed, src/train.py:110) folded with the rank, so replicas draw
+        # different masks like DataParallel's per-replica nn.Dropout
+        self.seed = _default_seed() if seed is None else int(seed)
+        self.dev_step = torch.zeros(1, device=self.device, dtype=torch.long)   # optimizer step counter (device truth)
+        self.dev_fwd = torch.zeros(1, device=self.device, dtype=torch.long)    # training forwards run (dropout RNG)
         self.dev_lr = torch.zeros(1, device=self.device, dtype=torch.float32)
-        self.host_step = 0
         self.dropout = "on"            # "on" | "off"
         self.grad_hook = None          # DDP: callable(engine, stage) invoked while backward is enqueued
         self.graphs = {}
@@ -729,8 +792,18 @@ class Engine:
         self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
         self.optimizer = "adam"        # 'adam' | 'rmsprop' | 'sgd' (train.py:218-231); set before the first graph capture
 
+    @property
+    def host_step(self) -> int:
+        """Optimizer steps taken.  The device counter is the only copy (graph replays advance it without the host
+        seeing them); reading it synchronises, which only checkpointing does."""
+        return int(self.dev_step.item())
+
+    @host_step.setter
+    def host_step(self, value: int):
+        self.dev_step.fill_(int(value))
+
     def plan(self, N, H, W) -> Plan:
-        key = (N, H, W)
+        key = (N, H, W, self.store.trainable_sig())
         p = self.plans.get(key)
         if p is None:
             p = Plan(self, N, H, W)
@@ -841,28 +914,28 @@ class Engine:
         stream = torch.cuda.current_stream().cuda_stream
         st = self.store
         dev_lr = self.dev_lr.data_ptr() if lr_on_device else None
-        self.host_step += 1
-        check(lib.mnb_counter_inc(self.dev_step.data_ptr(), stream), "counter_inc")
-        if self.optimizer == "sgd":
-            check(lib.mnb_sgd_step(st.flat.data_ptr(), st.grad.data_ptr(), st.total, float(lr), grad_scale, dev_lr,
-                                   stream), "sgd")
-        elif self.optimizer == "rmsprop":
-            _, v = st.adam_state()              # the second-moment buffer doubles as RMSprop's square_avg
-            check(lib.mnb_rmsprop_step(st.flat.data_ptr(), st.grad.data_ptr(), v.data_ptr(), st.total, float(lr),
-                                       0.99, 1e-8, grad_scale, dev_lr, stream), "rmsprop")
-        else:
+        if self.optimizer not in ("sgd", "rmsprop"):
             raise ValueError(f"unknown optimizer {self.optimizer!r}")
+        check(lib.mnb_counter_inc(self.dev_step.data_ptr(), stream), "counter_inc")
+        pp, gp = st.flat.data_ptr(), st.grad.data_ptr()
+        for lo, hi in st.trainable_ranges():    # only parameters with requires_grad are stepped (train.py:219)
+            if self.optimizer == "sgd":
+                check(lib.mnb_sgd_step(pp + 4 * lo, gp + 4 * lo, hi - lo, float(lr), grad_scale, dev_lr, stream), "sgd")
+            else:
+                _, v = st.adam_state()          # the second-moment buffer doubles as RMSprop's square_avg
+                check(lib.mnb_rmsprop_step(pp + 4 * lo, gp + 4 * lo, v.data_ptr() + 4 * lo, hi - lo, float(lr),
+                                           0.99, 1e-8, grad_scale, dev_lr, stream), "rmsprop")
 
     def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, lr_on_device=False):
         stream = torch.cuda.current_stream().cuda_stream
         m, v = self.store.adam_state()
-        self.host_step += 1
         check(lib.mnb_counter_inc(self.dev_step.data_ptr(), stream), "counter_inc")
         st = self.store
-        check(lib.mnb_adam_step(st.flat.data_ptr(), st.grad.data_ptr(), m.data_ptr(), v.data_ptr(), st.total,
-                                float(lr), betas[0], betas[1], eps, self.host_step, grad_scale,
-                                self.dev_lr.data_ptr() if lr_on_device else None,
-                                self.dev_step.data_ptr(), stream), "adam")
+        for lo, hi in st.trainable_ranges():    # only parameters with requires_grad are stepped (train.py:219)
+            check(lib.mnb_adam_step(st.flat.data_ptr() + 4 * lo, st.grad.data_ptr() + 4 * lo, m.data_ptr() + 4 * lo,
+                                    v.data_ptr() + 4 * lo, hi - lo, float(lr), betas[0], betas[1], eps, 1, grad_scale,
+                                    self.dev_lr.data_ptr() if lr_on_device else None,
+                                    self.dev_step.data_ptr(), stream), "adam")
 
     # ---- CUDA-graph replay of the whole step (single GPU): ~450 launches -> one graph launch ---------
     def train_step_graph(self, x, target, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
@@ -883,7 +956,7 @@ class Engine:
             raise RuntimeError("graph replay is single-GPU; use train_step with GradSync for data parallel")
         self._check_store()
         N, C, H, W = x.shape
-        key = (N, H, W)
+        key = (N, H, W, self.store.trainable_sig(), self.optimizer, self.dropout)
         g = self.graphs.get(key)
         if g is None:
             plan = self.plan(N, H, W)
@@ -897,13 +970,13 @@ class Engine:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             saved = (self.store.flat.clone(), self.store.fbuf.clone(), self.store.ibuf.clone(),
-                     self.dev_step.clone(), self.host_step, self.store.m.clone(), self.store.v.clone())
+                     self.dev_step.clone(), self.dev_fwd.clone(), self.store.m.clone(), self.store.v.clone())
             with torch.cuda.stream(s):
                 self._graph_body(sx, st, betas, eps)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.store.flat.copy_(saved[0]); self.store.fbuf.copy_(saved[1]); self.store.ibuf.copy_(saved[2])
-            self.dev_step.copy_(saved[3]); self.host_step = saved[4]
+            self.dev_step.copy_(saved[3]); self.dev_fwd.copy_(saved[4])
             self.store.m.copy_(saved[5]); self.store.v.copy_(saved[6])     # (a resumed optimizer state survives)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -935,6 +1008,21 @@ class Engine:
 
     def logits(self, plan):
         return plan.logits
+
+
+def _default_seed() -> int:
+    """torch's global seed (torch.manual_seed(args.seed), src/train.py:110) mixed with the data-parallel rank."""
+    import os
+    rank = 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank = dist.get_rank()
+        else:
+            rank = int(os.environ.get("RANK", "0"))
+    except Exception:
+        rank = 0
+    return (int(torch.initial_seed()) ^ (0x9E3779B97F4A7C15 * (rank + 1))) & 0x7FFFFFFFFFFFFFFF
 
 
 def _first_conv(module):

@@ -19,8 +19,15 @@ from oracle import mnasnet_oracle as O
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    backend = os.environ.get("MNB_DDP_BACKEND", "nccl")
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        # gloo moves CUDA tensors too: lets R ranks share ONE GPU, so the data-parallel path (bucket schedule,
+        # overlapped all-reduce, averaged gradients, lock-step Adam) is testable on a single-GPU box
+        torch.cuda.set_device(local % torch.cuda.device_count())
+        dist.init_process_group(backend)
     per, h, w = 4, 96, 96
     torch.manual_seed(42 + rank)              # deliberately different init per rank: broadcast must fix it
     with contextlib.redirect_stdout(io.StringIO()):
@@ -37,11 +44,12 @@ def main():
         torch.manual_seed(42)
         sd0 = O.init_state_dict()
         m.load_state_dict(sd0)
-    ddp.broadcast_parameters(eng)
-    sync = ddp.GradSync(eng)
+    wrapped = ddp.DataParallel(m)             # = nn.DataParallel(model) of src/train.py:202: broadcast + GradSync
+    assert wrapped.module is m and eng.grad_hook is wrapped.sync
+    assert all(k.startswith("module.") for k in wrapped.state_dict()) and len(wrapped.state_dict()) == 403
     x, t = O.synthetic_batch(per * world, h, w)
     xs, ts = x[rank * per:(rank + 1) * per].cuda(), t[rank * per:(rank + 1) * per].cuda()
-    out = m(xs)
+    out = wrapped(xs)
     loss = torch.nn.CrossEntropyLoss()(out, ts)
     loss.backward()                            # bucketed all-reduce overlapped with backward, averaged
     torch.cuda.synchronize()

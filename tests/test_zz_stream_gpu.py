@@ -137,7 +137,11 @@ def test_validate_matches_eval_forward_and_oracle():
 
 def test_resume_restores_model_and_optimizer_state():
     """a checkpoint in the reference's format, written after two fused steps, resumes into a fresh
-    model + engine (parameters, BN buffers, Adam moments, step counter): the third step is identical."""
+    model + engine.  The RESTORED state (parameters, BN buffers, Adam moments, step counter) is compared bit for bit;
+    the third step's loss to 1e-5.  Parameters AFTER that step are compared at 2*lr absolute: the step is not
+    run-to-run deterministic (fp32/fp64 atomics in split-K wgrad and the BN reductions), and Adam turns 1e-7 of
+    gradient noise on a near-zero gradient into a full +-lr move -- round 1 gated this at 1e-4 relative
+    and failed on features.0.bn.bias (1.8e-4) with the resume itself correct."""
     from mnb200 import checkpoint, engine
     from oracle import mnasnet_oracle as O
     x, t = O.synthetic_batch(4, 64, 64)
@@ -148,19 +152,25 @@ def test_resume_restores_model_and_optimizer_state():
         eng.train_step(xd, td, lr=1e-3)
     state = checkpoint.make_checkpoint(m, eng, epoch=3, best_loss=1.5)
     assert len(state["state_dict"]) == 403 and len(state["optimizer"]["state"]) == 112
-    l3 = eng.train_step(xd, td, lr=1e-3).item()
     m2 = _build("fp32", seed=7)
     eng2 = engine.engine_for(m2)
     epoch, best = checkpoint.resume(state, m2, eng2, load_optimizer=True)
     assert (epoch, best) == (3, 1.5) and eng2.host_step == 2
+    torch.cuda.synchronize()
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert torch.equal(eng.store.m, eng2.store.m) and torch.equal(eng.store.v, eng2.store.v)
+    l3 = eng.train_step(xd, td, lr=1e-3).item()
     l3b = eng2.train_step(xd, td, lr=1e-3).item()
     assert abs(l3 - l3b) <= 1e-5 * abs(l3)
     torch.cuda.synchronize()
     for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
         if k.endswith("conv.bias"):
             continue        # analytically zero gradient: Adam normalises rounding noise into a random walk (F9)
-        if a.dtype.is_floating_point:
+        if k.endswith("running_mean") or k.endswith("running_var"):
             assert rel(b, a) < 1e-4, k
+        elif a.dtype.is_floating_point:
+            assert (a - b).abs().max().item() <= 2e-3 + 1e-7, k
         else:
             assert torch.equal(a, b), k
 
