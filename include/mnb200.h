@@ -101,6 +101,22 @@ int mnb_dw_dgrad(const void* dz, const float* w, void* dx, const void* bn_z, con
                  void* stream);
 int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, const void* dz, float* dw,
                  int N, int H, int W, int C, int k, int dtype, void* stream);
+/* Fused backward of one depthwise ConvBlock (bf16 only; TMA + mma.sync kernel, csrc/dw_mma.cu): the BatchNorm-backward
+ * elementwise pass, conv backward-data, conv backward-weight and the BatchNorm-backward REDUCTIONS of the ConvBlock
+ * that produced this block's input, in one pass over dA, z and x (4 tensor passes instead of 9).  Replaces what autograd
+ * runs for ConvBlock.forward (src/models/mnasnet.py:58-62) of a depthwise block: threshold_backward +
+ * native_batch_norm_backward + convolution_backward, and the reductions of the next native_batch_norm_backward.
+ *   G  = dA * [scale*z + shift > 0]          sums = {sum G, sum G*z} of THIS block (mnb_bn_bwd_reduce or a fused producer)
+ *   dZ = a*G + b*z + c  (a, b, c from sums / save_mean / save_invstd / scale / m, as mnb_bn_bwd_apply_fused)
+ *   dgamma / dbeta / dbias += (each may be NULL)       dw[c,kh,kw] += sum dZ * relu(in_scale*x + in_shift) shifted
+ *   dx = conv backward-data of dZ                       (dw may be NULL: frozen weight)
+ *   in_sums[0:C] += sum dx', in_sums[C:2C] += sum dx'*x with dx' = dx * [in_scale*x + in_shift > 0]  (NULL = skip)
+ * x is the RAW output of the producing block (its BN scale / shift given as in_scale / in_shift, NULL = x is the
+ * activation itself and in_sums must be NULL).  Returns MNB_ERR_UNSUPPORTED for dtype != bf16. */
+int mnb_dw_bwd_fused(const void* dA, const void* z, const float* scale, const float* shift, const double* sums,
+                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* dbias,
+                     const void* x, const float* in_scale, const float* in_shift, const float* w, void* dx, float* dw,
+                     double* in_sums, int N, int H, int W, int C, int k, double m, int dtype, void* stream);
 
 /* ---- BatchNorm2d (train) : mnasnet.py:55,60 ; torch:nn/modules/batchnorm.py:163-178 ----------------------
  * finalize: mean/var from stats over m positions -> scale = gamma/sqrt(var+eps), shift = beta-mean*scale,

@@ -294,12 +294,31 @@ int dw_wgrad_stream(const void* x, const float* s, const float* t, const void* d
                     int C, int k, cudaStream_t st);
 }  // namespace mnb
 
+// TMA + mma.sync kernels (dw_mma.cu), option "dw_mma" (default 1): bf16 forward / stand-alone backward-data
+namespace mnb {
+int dw_fwd_mma(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z, double* stats,
+               int N, int H, int W, int C, int k, cudaStream_t st);
+int dw_dgrad_mma(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
+int dw_wgrad_mma(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C, int k,
+                 cudaStream_t st);
+int dw_bwd_mma(const void* G, const void* Z, const float* scale, const float* shift, const double* sums, const float* mean,
+               const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
+               const float* in_scale, const float* in_shift, const float* w, void* dX, float* dw, double* nsums, int N, int H,
+               int W, int C, int k, cudaStream_t st);
+}  // namespace mnb
+
 extern "C" {
 
 int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                void* z, double* stats, int N, int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_fwd", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    // tensor-pipe kernel from 14-row maps up (7x7 / 4x4 maps fill 16-pixel strips too poorly: tile kernel); dw_mma = 2 forces it
+    if (dtype == MNB_BF16 && !bias && !use_dw_stream(0, H, k) &&
+        (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12))) {
+        int r = dw_fwd_mma(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16 && use_dw_stream(0, H, k)) {
         int r = dw_fwd_stream(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -325,6 +344,11 @@ int mnb_dw_dgrad(const void* dz, const float* w, void* dx, const void* bn_z, con
     MNB_REQUIRE(!bn_z || (bn_scale && bn_shift && bn_sums), "dw_dgrad: bn_z needs bn_scale/bn_shift/bn_sums");
     if (!bn_z) bn_sums = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_BF16 && !bn_z && !use_dw_stream(1, H, k) &&
+        (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12))) {
+        int r = dw_dgrad_mma(dz, w, dx, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16 && !bn_z && use_dw_stream(1, H, k)) {
         int r = dw_dgrad_stream(dz, w, dx, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -348,6 +372,13 @@ int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, co
                  int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_wgrad", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    // tensor-pipe backward-weight where it measured faster than the tile kernel: 3x3 on >= 56-row maps with the 24-channel
+    // geometry (5x5 needs 15 MMAs per 128 products and runs no faster than the CUDA-core kernel)
+    if (dtype == MNB_BF16 && !use_dw_stream(2, H, k) &&
+        (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && k == 3 && H >= 56 && W >= 24 && C % 24 == 0))) {
+        int r = dw_wgrad_mma(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16 && use_dw_stream(2, H, k)) {
         int r = dw_wgrad_stream(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -365,6 +396,20 @@ int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, co
     }
     MNB_LAUNCH_CHECK("dw_wgrad");
     return 0;
+}
+
+int mnb_dw_bwd_fused(const void* dA, const void* z, const float* scale, const float* shift, const double* sums,
+                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* dbias,
+                     const void* x, const float* in_scale, const float* in_shift, const float* w, void* dx, float* dw,
+                     double* in_sums, int N, int H, int W, int C, int k, double m, int dtype, void* stream) {
+    if (int e = check_dw("dw_bwd_fused", N, H, W, C, k, dtype)) return e;
+    MNB_REQUIRE(dA && z && scale && shift && sums && save_mean && save_invstd && x && w && dx, "dw_bwd_fused: NULL operand");
+    MNB_REQUIRE(!in_sums || in_scale, "dw_bwd_fused: in_sums needs in_scale / in_shift");
+    MNB_REQUIRE(!in_scale || in_shift, "dw_bwd_fused: in_scale without in_shift");
+    MNB_REQUIRE(m > 0, "dw_bwd_fused: bad element count");
+    if (dtype != MNB_BF16) { set_error("dw_bwd_fused: bf16 only"); return MNB_ERR_UNSUPPORTED; }
+    return dw_bwd_mma(dA, z, scale, shift, sums, save_mean, save_invstd, m, dgamma, dbeta, dbias, x, in_scale, in_shift, w,
+                      dx, dw, in_sums, N, H, W, C, k, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -520,6 +520,24 @@ class Plan:
                 conv, bn = a.cb.conv, a.cb.bn
                 M, C = int(a.m), a.Cout
                 self._cur_detail = f"{a.inp.H}x{a.inp.W} {a.inp.C}->{a.Cout} k{a.k}s{a.stride}"
+                if self._fused_dw_backward(a, idx, first_live):
+                    # one kernel: BN-backward elementwise pass + backward-data + backward-weight of this depthwise
+                    # block + the BN-backward reductions of the block that produced its input (csrc/dw_mma.cu)
+                    r = a.inp
+                    pa = self.apps[a.index - 1]
+                    if not a.reduce_fused:
+                        self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
+                                 nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
+                    dx = take()
+                    self._op(ops, "mnb_dw_bwd_fused", gbuf, a.z, a.scale, a.shift, a.sums, a.mean, a.invstd,
+                             Gp(bn.weight), Gp(bn.bias), Gp(conv.bias), r.t, r.scale, r.shift, conv.weight, dx,
+                             Gp(conv.weight), pa.sums, r.N, r.H, r.W, C, a.k, a.m, self.code,
+                             nbytes=4 * a.out_bytes, label=a.label + "_bwd_fused")
+                    pa.reduce_fused = True
+                    if not any(gbuf is h for h in held):
+                        free.append(gbuf)
+                    gbuf = dx
+                    continue
                 dz = take()
                 if not a.reduce_fused:     # else: done in the epilogue of the dgrad that produced gbuf
                     self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
@@ -581,6 +599,22 @@ class Plan:
         self.sub_din = gbuf
         if side and getattr(self, "side_last", None) is not None:
             ops.append(_EventOp("wait", self.side_last, 0))      # join: optimizer / caller see all weight grads
+
+    def _fused_dw_backward(self, a, idx, first_live) -> bool:
+        """Where the fused depthwise backward kernel is used: bf16, 3x3 on maps of >= 56 rows with a channel count the
+        24-channel geometry tiles exactly -- the layers where it measured faster than the unfused chain
+        (profiles/r2_exp_dw_mma.json); the input must come straight from a ConvBlock (raw z + scale / shift)."""
+        eng = self.eng
+        if eng.dtype != "bf16" or not eng.fuse_dw_bwd or a.kind != "dw":
+            return False
+        r = a.inp
+        if r.scale is None or a.index == 0 or self.apps[a.index - 1].z is not r.t:
+            return False
+        if not (a.need_dgrad and idx > first_live):
+            return False
+        if eng.fuse_dw_bwd == 2:                 # forced (tests): every shape the kernel supports
+            return r.H >= 1
+        return a.k == 3 and r.H >= 56 and r.W >= 24 and a.Cout % 24 == 0
 
     def _new_event(self):
         self.n_events += 1
@@ -789,6 +823,7 @@ class Engine:
         self.side_stream = torch.cuda.Stream(device=self.device)
         self.fuse_bn_reduce = False    # BN-backward reductions in the producing dgrad epilogue (tested; off:
                                        # the dgrad epilogues are the bottleneck, the separate kernel is faster)
+        self.fuse_dw_bwd = 1           # fused depthwise ConvBlock backward (csrc/dw_mma.cu): 0 off, 1 where it wins, 2 always
         self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
         self.optimizer = "adam"        # 'adam' | 'rmsprop' | 'sgd' (train.py:218-231); set before the first graph capture
 
@@ -1090,6 +1125,15 @@ def configure(module: Optional[nn.Module] = None, dtype: Optional[str] = None, i
         tgt["impl"] = impl
     if module is not None and module in _ENGINES:
         del _ENGINES[module]
+
+
+def release(module: nn.Module):
+    """Drops the engine of a module (plans, activation buffers, CUDA graphs).  The engine references the module, so
+    the weak registry alone never frees it; long-running scripts that build many models call this."""
+    eng = _ENGINES.pop(module, None)
+    if eng is not None:
+        eng.plans.clear()
+        eng.graphs.clear()
 
 
 def engine_for(module: nn.Module) -> Engine:

@@ -249,7 +249,11 @@ def test_depthwise_fwd_dgrad_wgrad(case, dtype):
     dx2 = torch.empty_like(dx)
     L.call("mnb_dw_dgrad", P(dzd), P(wd), P(dx2), None, None, None, None, N, H, W, C, k, code(dtype), stream())
     torch.cuda.synchronize()
-    assert torch.equal(dx, dx2)
+    if dtype == "fp32":
+        assert torch.equal(dx, dx2)
+    else:   # without the fused reduction bf16 maps of >= 12 rows take the tensor-pipe kernel (bf16 weights): same math,
+        # one more rounding of the taps
+        assert rel(dx2.float(), dx.float()) < 5e-3
     dw = torch.zeros(C, 1, k, k, device="cuda")
     L.call("mnb_dw_wgrad", P(xd), P(sd), P(td), P(dzd), P(dw), N, H, W, C, k, code(dtype), stream())
     torch.cuda.synchronize()
