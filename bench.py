@@ -12,8 +12,11 @@ scaling for N > 1 = configs[2] at 256/GPU).  Prints ONE JSON line on rank 0.
   e2e      the reference's own loop (src/train.py:427-440: .to(device), model(input), criterion, zero_grad,
            backward, optimizer.step) through the drop-in modules with pinned HOST inputs: the H2D copy of every
            step's batch and the D2H read of its loss are inside the timed region
-  roofline dominant kernel class: algorithmic bytes / CUDA-event time per launch vs MEASURED_PEAKS.json
+  roofline dominant kernel FAMILY of the step (depthwise / pointwise / dense 3x3; the BatchNorm passes carry no
+           algorithmic bytes of their own under SURVEY.md section 8d): section-8d bytes of that family's conv calls /
+           CUDA-event time of its launches vs MEASURED_PEAKS.json; `families` holds the same for every family
   cpu_baseline  the CPU oracle (port of the reference loop, fp32, torch CPU kernels) on the host's cores
+  gpu_eager_baseline  the same architecture through stock PyTorch eager on this GPU (bf16 autocast, channels_last)
 """
 import argparse
 import json
@@ -143,6 +146,71 @@ def cpu_baseline(seconds_budget=20.0):
     return {"value": nb / med, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"BASELINE configs[0]: batch {nb}, 3x224x224 fp32 fwd+CE+bwd+Adam, median of {len(times)} "
                       f"steps after 2 warm-up ({med * 1e3:.0f} ms/step)"}
+
+
+def gpu_eager_baseline(n, size, steps=5, warm=3):
+    """Stock PyTorch on the same GPU: the reference's architecture and loop (oracle port = the reference's own torch
+    ops; a checker-side baseline like cpu_baseline, never on the product path) under bf16 autocast + channels_last,
+    cuDNN autotuned.  This is what the reference would run on a B200 today."""
+    import torch
+    from oracle import mnasnet_oracle as O
+    try:
+        old = torch.backends.cudnn.benchmark
+        torch.backends.cudnn.benchmark = True
+        torch.manual_seed(42)
+        sd = {k: v.cuda() for k, v in O.init_state_dict().items()}
+        tr = O.Trainer(sd)
+        x = torch.randn(n, 3, size, size, device="cuda").contiguous(memory_format=torch.channels_last)
+        t = torch.randint(0, 1000, (n,), device="cuda")
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return tr.step(x, t, dropout_masks=None)
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        torch.backends.cudnn.benchmark = old
+        del tr, sd, x
+        torch.cuda.empty_cache()
+        return {"value": n / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+                "what": f"torch {torch.__version__} eager, autocast bf16 + channels_last, cuDNN benchmark, batch {n}, "
+                        f"{steps} steps after {warm} warm-up, same GPU"}
+    except Exception as e:          # never lose the main measurement over a context number
+        return {"value": None, "error": repr(e)[:200]}
+
+
+FAMILIES = ("depthwise", "pointwise", "dense3x3", "batchnorm", "other")
+
+
+def family_of(label):
+    if label.startswith("dw"):
+        return "depthwise"
+    if label.startswith("pw1x1"):
+        return "pointwise"
+    if label.startswith("conv3x3"):
+        return "dense3x3"
+    if label.startswith("bn_") or label.startswith("mnb_bn_"):
+        return "batchnorm"
+    return "other"
+
+
+def algorithmic_work(plan):
+    """SURVEY.md section 8d per family for this plan's shapes: bytes = fwd (|X|+|Y|) + bwd (2|X|+2|Y|) per conv call at
+    the stored element size, flops = 6 * MACs (fwd 2, bwd 4)."""
+    out = {f: {"bytes": 0.0, "flops": 0.0} for f in FAMILIES}
+    for a in plan.apps:
+        conv = a.cb.conv
+        fam = "depthwise" if a.kind == "dw" else ("pointwise" if a.k == 1 else "dense3x3")
+        out[fam]["bytes"] += 3.0 * (a.in_bytes + a.out_bytes)
+        out[fam]["flops"] += 6.0 * a.m * a.Cout * a.k * a.k * (conv.in_channels // conv.groups)
+    return out
 
 
 def main():
@@ -322,35 +390,59 @@ def main():
             q = per_op.setdefault((label, detail), [0, 0.0, 0])
             q[0] += 1; q[1] += ms_; q[2] += nbytes
         tot = sum(v[1] for v in agg.values())
-        table = sorted(({"kernel": k, "launches_per_step": v[0] // 3, "ms_per_step": v[1] / 3,
-                         "share": v[1] / tot, "algorithmic_GB_per_step": v[2] / 3 / 1e9,
+        table = sorted(({"kernel": k, "family": family_of(k), "launches_per_step": v[0] // 3, "ms_per_step": v[1] / 3,
+                         "share": v[1] / tot, "kernel_traffic_GB_per_step": v[2] / 3 / 1e9,
                          "achieved_GBps": (v[2] / 1e9) / (v[1] / 1e3) if v[1] > 0 else 0.0,
                          "frac_of_hbm_peak": ((v[2] / 1e9) / (v[1] / 1e3)) / hbm if v[1] > 0 else 0.0}
                         for k, v in agg.items()), key=lambda r: -r["ms_per_step"])
-        top = next(r for r in table if r["algorithmic_GB_per_step"] > 0)
-        traffic = None
-        try:    # dram__bytes_read+write per step for this kernel class, from the committed ncu pass (profiles/)
-            with open(os.path.join(ROOT, "profiles", "r1_ncu_step_summary.json")) as f:
-                traffic = json.load(f)["classes"][top["kernel"]]["dram_GB_per_step"]
+        # per family: time of its launches (CUDA events) vs the section-8d algorithmic bytes / flops of its conv calls
+        work = algorithmic_work(eng.plan(N, S, S))
+        ncu = None
+        try:    # dram__bytes_read+write per kernel class from the committed ncu pass of the same command (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r2_ncu_step_summary.json")) as f:
+                ncu = json.load(f)["classes"]
         except Exception:
-            traffic = None
-        roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_GBps"], "peak": hbm,
-                "unit": "GB/s", "frac": top["achieved_GBps"] / hbm, "traffic": traffic,
-                "traffic_unit": "GB per step over this kernel class's launches (ncu dram__bytes_read+write)",
-                "peak_source": which,
-                "share_of_step": top["share"],
-                "step_algorithmic_GB": sum(r["algorithmic_GB_per_step"] for r in table),
-                "step_frac_of_hbm_peak": (value / world) * 117.17e6 / 1e9 / hbm}
+            ncu = None
+        families = {}
+        for fam in FAMILIES:
+            ms_f = sum(r["ms_per_step"] for r in table if r["family"] == fam)
+            gb, gf = work[fam]["bytes"] / 1e9, work[fam]["flops"] / 1e9
+            d = {"ms_per_step": ms_f, "share": ms_f * 3 / tot, "algorithmic_GB": gb, "algorithmic_GFLOP": gf}
+            if ms_f > 0 and gb > 0:
+                d["achieved_GBps"] = gb / (ms_f / 1e3)
+                d["frac_of_hbm_peak"] = d["achieved_GBps"] / hbm
+                d["achieved_TFLOPs"] = gf / ms_f
+                d["frac_of_bf16_peak"] = d["achieved_TFLOPs"] / tf
+            if ncu is not None:
+                tr_ = [ncu[r["kernel"]]["dram_GB_per_step"] for r in table if r["family"] == fam and r["kernel"] in ncu]
+                d["dram_GB_ncu"] = sum(tr_) if tr_ else None
+            families[fam] = d
+        families["batchnorm"]["note"] = "BN-backward / residual passes: 0 algorithmic bytes of their own under section 8d"
+        top_f = max(("depthwise", "pointwise", "dense3x3"), key=lambda f_: families[f_]["ms_per_step"])
+        top = families[top_f]
+        roof = {"bound": "hbm", "kernel": top_f + " family: " + ", ".join(sorted(
+                    {r["kernel"] for r in table if r["family"] == top_f})),
+                "achieved": top["achieved_GBps"], "peak": hbm, "unit": "GB/s", "frac": top["frac_of_hbm_peak"],
+                "traffic": top.get("dram_GB_ncu"),
+                "traffic_unit": "GB per step over this family's launches (ncu dram__bytes_read+write, profiles/r2_ncu_step_summary.json)",
+                "algorithmic_GB_per_step": top["algorithmic_GB"], "ms_per_step": top["ms_per_step"],
+                "peak_source": which, "share_of_step": top["share"],
+                "families": families,
+                "step_algorithmic_GB": sum(families[f_]["algorithmic_GB"] for f_ in FAMILIES),
+                "step_kernel_traffic_GB": sum(r["kernel_traffic_GB_per_step"] for r in table),
+                "step_frac_of_hbm_peak": (value / world) * sum(families[f_]["algorithmic_GB"] for f_ in FAMILIES) / N / hbm}
         if args.profile_out:
             with open(args.profile_out, "w") as f:
                 layers = sorted(({"kernel": k[0], "layer": k[1], "launches_per_step": v[0] // 3,
                                   "ms_per_step": v[1] / 3, "algorithmic_GB_per_step": v[2] / 3 / 1e9,
                                   "achieved_GBps": (v[2] / 1e9) / (v[1] / 1e3) if v[1] > 0 else 0.0}
                                  for k, v in per_op.items()), key=lambda r: -r["ms_per_step"])
-                json.dump({"ms_per_step_sum": tot / 3, "kernels": table, "layers": layers[:80]}, f, indent=1)
+                json.dump({"ms_per_step_sum": tot / 3, "families": families, "kernels": table, "layers": layers[:120]},
+                          f, indent=1)
 
-    cpu = None
+    cpu, eager = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        eager = gpu_eager_baseline(N, S)
         cpu = cpu_baseline()
 
     if rank == 0:
@@ -364,7 +456,7 @@ def main():
                            "l2": "no flush needed: each step streams a 154 MB input batch (2 alternating "
                                  "buffers) and ~6 GB of activations, both >> 126 MB L2"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "final_loss": last_loss}
+                "gpu_eager_baseline": eager, "final_loss": last_loss}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -374,7 +466,7 @@ def _kernel_options():
     """Which kernel families `impl` auto selects (mnb_get_option): recorded with every bench line."""
     try:
         from mnb200 import _lib
-        return {n: _lib.get_option(n) for n in ("pw_stream", "stem_mma", "dw_stream", "dw_stream_pd", "dw_stream_tw8")}
+        return {n: _lib.get_option(n) for n in ("pw_stream", "stem_mma", "dw_stream", "dw_mma")}
     except Exception as e:      # never lose a measurement over a label
         return {"error": str(e)}
 
