@@ -646,14 +646,9 @@ __device__ __forceinline__ void dwb_load_x(const DwbWg& q, int xrow, uint32_t (&
 }
 
 template <int K, int CG, int TWS, int KH0, int KH1>
-__device__ __forceinline__ void dwb_wgrad_pass(const DwbWg& q, float* dst, int g, int t) {
+__device__ __forceinline__ void dwb_wgrad_rows(const DwbWg& q, float (&wacc)[KH1 - KH0][(K + 1) / 2][4]) {
     using Cfg = DwmCfg<K, CG, TWS>;
     constexpr int RB = Cfg::RB, PITCH = Cfg::PITCH, NPR = (K + 1) / 2, R = KH1 - KH0;
-    float wacc[R][NPR][4];
-#pragma unroll
-    for (int a = 0; a < R; ++a)
-#pragma unroll
-        for (int pr = 0; pr < NPR; ++pr) wacc[a][pr][0] = wacc[a][pr][1] = wacc[a][pr][2] = wacc[a][pr][3] = 0.f;
     uint32_t bf[R][2];
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
@@ -680,8 +675,13 @@ __device__ __forceinline__ void dwb_wgrad_pass(const DwbWg& q, float* dst, int g
                 }
         }
     }
-    // the diagonal c' == c lives on the lanes with t == g >> 1: slot A in d[g & 1], slot B in d[2 + (g & 1)];
-    // shift s of the dZ operand is tap column K-1-s, kh is the tap row
+}
+
+// the diagonal c' == c lives on the lanes with t == g >> 1: slot A in d[g & 1], slot B in d[2 + (g & 1)];
+// shift s of the dZ operand is tap column K-1-s, kh is the tap row
+template <int K, int KH0, int KH1>
+__device__ __forceinline__ void dwb_wgrad_flush(const float (&wacc)[KH1 - KH0][(K + 1) / 2][4], float* dst, int g, int t) {
+    constexpr int NPR = (K + 1) / 2;
     if ((g >> 1) == t) {
 #pragma unroll
         for (int kh = KH0; kh < KH1; ++kh)
@@ -692,6 +692,108 @@ __device__ __forceinline__ void dwb_wgrad_pass(const DwbWg& q, float* dst, int g
                     atomicAdd(dst + kh * K + (K - 2 - 2 * pr), (g & 1) ? wacc[kh - KH0][pr][3] : wacc[kh - KH0][pr][2]);
             }
     }
+}
+
+template <int K, int CG, int TWS, int KH0, int KH1>
+__device__ __forceinline__ void dwb_wgrad_pass(const DwbWg& q, float* dst, int g, int t) {
+    constexpr int NPR = (K + 1) / 2, R = KH1 - KH0;
+    float wacc[R][NPR][4];
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+        for (int pr = 0; pr < NPR; ++pr) wacc[a][pr][0] = wacc[a][pr][1] = wacc[a][pr][2] = wacc[a][pr][3] = 0.f;
+    dwb_wgrad_rows<K, CG, TWS, KH0, KH1>(q, wacc);
+    dwb_wgrad_flush<K, KH0, KH1>(wacc, dst, g, t);
+}
+
+// Stand-alone backward-weight: dZ (with the horizontal halo) and X boxes double-buffered, one barrier per step, the
+// accumulators stay in registers for the CTA's whole life (its channel group never changes) and are flushed once.
+template <int K, int CG, int TWS>
+__global__ void __launch_bounds__(DwmCfg<K, CG, TWS>::THREADS)
+    dw_mma_wgrad_k(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_gp,
+                   const __grid_constant__ CUtensorMap tm_x, const DwbP p) {
+    using Cfg = DwmCfg<K, CG, TWS>;
+    using B = DwbCfg<K, CG, TWS>;
+    constexpr int P = Cfg::P, RB = Cfg::RB, NCH = Cfg::NCH, TW = Cfg::TW, PITCH = Cfg::PITCH;
+    constexpr int THREADS = Cfg::THREADS, KK = K * K, NPR = (K + 1) / 2, STAGE = B::GB_BYTES + B::XB_BYTES;
+    extern __shared__ __align__(128) unsigned char dsm[];
+    const uint32_t S0 = smem_u32(dsm);
+    float* dwacc = reinterpret_cast<float*>(dsm + 2 * STAGE);                    // [CG][KK]
+    const uint32_t bar0 = S0 + 2 * STAGE + B::DW_BYTES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int chunk = warp % NCH, strip = warp / NCH;
+    const int cb = blockIdx.x % p.cblocks, slot = blockIdx.x / p.cblocks, nslots = gridDim.x / p.cblocks;
+    const int cbase = cb * CG;
+    const int ch = cbase + chunk * 8 + g;
+    const bool chunk_live = cbase + chunk * 8 < p.C;
+    if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+    for (int i = tid; i < CG * KK; i += THREADS) dwacc[i] = 0.f;
+    const bool act_in = p.in_scale != nullptr;
+    const float sg = (act_in && chunk_live) ? p.in_scale[ch] : 1.f, tg = (act_in && chunk_live) ? p.in_shift[ch] : 0.f;
+    const int mi = lane >> 3, r8 = lane & 7;
+    const uint32_t off4 = (uint32_t)(((mi >> 1) + (mi & 1) * 8 + r8 + strip * 16) * PITCH + chunk * 16);
+    const uint32_t off2 = (uint32_t)(((K - 1) + (mi & 1) * 8 + r8 + strip * 16) * PITCH + chunk * 16);
+    const uint32_t offx = (uint32_t)(((mi & 1) * 8 + r8 + strip * 16) * PITCH + chunk * 16);
+    float wacc[K][NPR][4];
+#pragma unroll
+    for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int pr = 0; pr < NPR; ++pr) wacc[a][pr][0] = wacc[a][pr][1] = wacc[a][pr][2] = wacc[a][pr][3] = 0.f;
+    uint32_t ph = 0;
+    __syncthreads();
+
+    // a segment's prologue rows belong to the segment above, except the K/2 rows above block 0
+    auto first_j = [](const DwmStep& s) { return s.jb0 == 0 ? -1 : s.jb0; };
+    auto issue = [&](const DwmStep& s, int b) {
+        const bool pro = s.j < s.jb0;
+        const int row_first = pro ? RB * s.jb0 - P : RB * s.j + P;
+        if (row_first < p.H) {
+            const uint32_t gb = S0 + b * STAGE;
+            mbar_expect_tx(bar0 + 8 * b, (uint32_t)((pro ? K - 1 : RB) * Cfg::ROWB + B::XROWS * Cfg::OROWB));
+            tma_load4(gb, pro ? &tm_gp : &tm_g, cbase, s.w0 - P, row_first, s.n, bar0 + 8 * b);
+            tma_load4(gb + B::GB_BYTES, &tm_x, cbase, s.w0, RB * s.j, s.n, bar0 + 8 * b);
+        }
+    };
+    DwmStep cur, nxt;
+    dwm_step_init<TW>(cur, slot, p.items, p.nseg, p.tiles_w, p.seg, p.nblocks);
+    if (cur.item < p.items) cur.j = first_j(cur);
+    if (tid == 0 && cur.item < p.items) issue(cur, 0);
+    int b = 0;
+    while (cur.item < p.items) {
+        nxt = cur;
+        if (++nxt.j >= nxt.jb1) {
+            dwm_step_init<TW>(nxt, nxt.item + nslots, p.items, p.nseg, p.tiles_w, p.seg, p.nblocks);
+            if (nxt.item < p.items) nxt.j = first_j(nxt);
+        }
+        if (tid == 0 && nxt.item < p.items) issue(nxt, b ^ 1);      // released by the previous step's barrier
+        const bool pro = cur.j < cur.jb0;
+        const int rbase = RB * cur.j + P;
+        const int row_first = pro ? RB * cur.jb0 - P : rbase;
+        if (row_first < p.H) {
+            mbar_wait(bar0 + 8 * b, (ph >> b) & 1);
+            ph ^= 1u << b;
+            const int sw = cur.w0 + strip * 16;
+            if (chunk_live && sw < p.W) {
+                const uint32_t gb = S0 + b * STAGE;
+                const uint32_t base = pro ? gb - (uint32_t)((RB - (K - 1)) * Cfg::ROWB) : gb;
+                DwbWg q;
+                q.gz4 = base + off4; q.gz2 = base + off2; q.xrow = gb + B::GB_BYTES + offx;
+                const int c0 = sw + 2 * t;
+                q.cm0 = (c0 < p.W ? 0x0000ffffu : 0u) | (c0 + 1 < p.W ? 0xffff0000u : 0u);
+                q.cm1 = (c0 + 8 < p.W ? 0x0000ffffu : 0u) | (c0 + 9 < p.W ? 0xffff0000u : 0u);
+                q.ag = f2_pack(sg, sg); q.at = f2_pack(tg, tg); q.act = act_in;
+                q.xrow_img0 = RB * cur.j; q.rbase = rbase; q.i0 = pro ? RB - (K - 1) : 0; q.H = p.H;
+                dwb_wgrad_rows<K, CG, TWS, 0, K>(q, wacc);
+            }
+        }
+        __syncthreads();
+        cur = nxt;
+        b ^= 1;
+    }
+    if (chunk_live) dwb_wgrad_flush<K, 0, K>(wacc, dwacc + (chunk * 8 + g) * KK, g, t);
+    __syncthreads();
+    for (int i = tid; i < CG * KK; i += THREADS)
+        if (cbase + i / KK < p.C) atomicAdd(&p.dw[(size_t)cbase * KK + i], dwacc[i]);
 }
 
 // WGO: backward-weight only -- the G box already holds dZ (no Z box, no transform, no backward-data, no store)
@@ -998,6 +1100,49 @@ int dw_bwd_mma(const void* G, const void* Z, const float* scale, const float* sh
     return MNB_ERR_UNSUPPORTED;
 }
 
+template <int K, int CG, int TWS>
+static int launch_wgrad_cfg(const DwmGeom& g, const DwbP& p0, const void* dZ, const void* X, cudaStream_t st,
+                            const char* name) {
+    using Cfg = DwmCfg<K, CG, TWS>;
+    using B = DwbCfg<K, CG, TWS>;
+    constexpr int RB = Cfg::RB;
+    constexpr int SMEM = 2 * (B::GB_BYTES + B::XB_BYTES) + B::DW_BYTES + 16;
+    DwbP p = p0;
+    const int N = p.N, H = p.H, W = p.W, C = p.C;
+    CUtensorMap tm_g, tm_gp, tm_x;
+    if (int e = dwm_tensor_map(&tm_g, dZ, N, H, W, C, CG, Cfg::HC, RB)) return e;
+    if (int e = dwm_tensor_map(&tm_gp, dZ, N, H, W, C, CG, Cfg::HC, K - 1)) return e;
+    if (int e = dwm_tensor_map(&tm_x, X, N, H, W, C, CG, Cfg::TW, B::XROWS)) return e;
+    p.tiles_w = g.tiles_w; p.cblocks = g.cblocks;
+    p.nblocks = (H + RB - 1) / RB;
+    static int occ = -1;
+    if (occ < 0) {
+        cudaError_t e = cudaFuncSetAttribute(dw_mma_wgrad_k<K, CG, TWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dw_mma_wgrad_k<K, CG, TWS>, B::THREADS, SMEM);
+        if (o < 1) { set_error("%s: kernel does not fit on an SM", name); return MNB_ERR_UNSUPPORTED; }
+        occ = o;
+    }
+    const long long cols = (long long)N * g.tiles_w;
+    if (cols > (1 << 24)) { set_error("%s: too many columns", name); return MNB_ERR_UNSUPPORTED; }
+    const long long slots_max = ((long long)num_sms() * occ + g.cblocks - 1) / g.cblocks;
+    int seg = option_get(OPT_DW_MMA_SEG);
+    if (seg <= 0) {
+        seg = p.nblocks;
+        while (seg > 2 && cols * ((p.nblocks + seg - 1) / seg) < 6 * slots_max) seg = (seg + 1) / 2;
+    }
+    if (seg > p.nblocks) seg = p.nblocks;
+    p.seg = seg;
+    p.nseg = (p.nblocks + seg - 1) / seg;
+    p.items = (int)(cols * p.nseg);
+    long long slots = slots_max;
+    if (slots > p.items) slots = p.items;
+    dw_mma_wgrad_k<K, CG, TWS><<<(unsigned)(slots * g.cblocks), B::THREADS, SMEM, st>>>(tm_g, tm_gp, tm_x, p);
+    MNB_LAUNCH_CHECK(name);
+    return 0;
+}
+
 // backward-weight alone on the tensor pipe: dw[c,kh,kw] += sum dz * relu(s*x+t) shifted
 int dw_wgrad_mma(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C, int k,
                  cudaStream_t st) {
@@ -1005,7 +1150,7 @@ int dw_wgrad_mma(const void* x, const float* s, const float* t, const void* dz, 
     p.in_scale = s; p.in_shift = t; p.dw = dw; p.N = N; p.H = H; p.W = W; p.C = C; p.m = 1.0;
     const DwmGeom g = dwm_geometry(C, W, k);
     const char* name = "dw_wgrad(mma)";
-#define MNB_DWB(KK, CGG, TT) return launch_bwd_cfg<KK, CGG, TT, true>(g, p, dz, nullptr, x, nullptr, st, name)
+#define MNB_DWB(KK, CGG, TT) return launch_wgrad_cfg<KK, CGG, TT>(g, p, dz, x, st, name)
     if (k == 3) {
         if (g.CG == 24 && g.TWS == 1) MNB_DWB(3, 24, 1);
         if (g.CG == 24 && g.TWS == 2) MNB_DWB(3, 24, 2);

@@ -372,10 +372,10 @@ int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, co
                  int H, int W, int C, int k, int dtype, void* stream) {
     if (int e = check_dw("dw_wgrad", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    // tensor-pipe backward-weight where it measured faster than the tile kernel: 3x3 on >= 56-row maps with the 24-channel
-    // geometry (5x5 needs 15 MMAs per 128 products and runs no faster than the CUDA-core kernel)
+    // tensor-pipe backward-weight where it measured faster than the tile kernel (profiles/r2_exp_dw_mma.json): maps of
+    // >= 12 rows whose channel count the 24-channel geometry tiles exactly (not the 32-channel stem block)
     if (dtype == MNB_BF16 && !use_dw_stream(2, H, k) &&
-        (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && k == 3 && H >= 56 && W >= 24 && C % 24 == 0))) {
+        (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12 && C % 24 == 0))) {
         int r = dw_wgrad_mma(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
