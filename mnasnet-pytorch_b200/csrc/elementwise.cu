@@ -20,12 +20,12 @@ void set_error(const char* fmt, ...) {
 }
 
 // kernel-selection switches: -1 = not set yet (the environment variable is consulted once, then the built-in default)
-static int g_opt[OPT_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+static int g_opt[OPT_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 static const char* const g_opt_name[OPT_COUNT] = {"pw_stream", "stem_mma", "dw_stream", "dw_stream_pd", "dw_stream_tw8",
-                                                   "dw_mma", "dw_mma_cg", "dw_mma_tws", "dw_mma_seg"};
+                                                   "dw_mma", "dw_mma_cg", "dw_mma_tws", "dw_mma_seg", "bn_ctas"};
 static const char* const g_opt_env[OPT_COUNT] = {"MNB_PW_STREAM", "MNB_STEM_MMA", "MNB_DW_STREAM", "MNB_DW_STREAM_PD", "MNB_DW_STREAM_TW8",
-                                                  "MNB_DW_MMA", "MNB_DW_MMA_CG", "MNB_DW_MMA_TWS", "MNB_DW_MMA_SEG"};
-static const int g_opt_default[OPT_COUNT] = {1, 1, 0, 1, 0, 1, 0, 0, 0};
+                                                  "MNB_DW_MMA", "MNB_DW_MMA_CG", "MNB_DW_MMA_TWS", "MNB_DW_MMA_SEG", "MNB_BN_CTAS"};
+static const int g_opt_default[OPT_COUNT] = {1, 1, 0, 1, 0, 1, 0, 0, 0, 0};
 int option_get(int id) {
     if (g_opt[id] < 0) {
         const char* e = getenv(g_opt_env[id]);
@@ -40,14 +40,16 @@ int option_get(int id) {
 struct ColGeom {
     dim3 grid, block;
 };
-static ColGeom col_geom(long long M, int C, int ctas_per_sm = 8) {
+// min_rows: rows every thread should get at least (amortises per-thread constants and the per-CTA flush on small tensors)
+static ColGeom col_geom(long long M, int C, int ctas_per_sm = 8, int min_rows = 1) {
     int cv = C / 8;
     int tx = largest_divisor_le(cv, 32);
     int ty = 256 / tx;
-    long long gy = cdiv(M, ty);
+    long long gy = cdiv(M, (long long)ty * min_rows);
     long long cap = (long long)num_sms() * ctas_per_sm / (cv / tx);
     if (cap < 1) cap = 1;
     if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
     ColGeom g;
     g.grid = dim3(cv / tx, (unsigned)gy);
     g.block = dim3(tx, ty);
@@ -697,7 +699,7 @@ int mnb_bn_bwd_apply_fused(const void* dA, const void* z, const float* scale, co
                            const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* dbias,
                            void* dZ, long long M, int C, double m, int dtype, void* stream) {
     MNB_REQUIRE(C % 8 == 0 && M > 0 && m > 0, "bn_bwd_apply_fused: bad shape");
-    ColGeom g = col_geom(M, C, 16);
+    ColGeom g = col_geom(M, C, 16, 16);     // >= 16 rows per thread: each thread derives its channels' coefficients first
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MNB_F32) bn_bwd_apply_fused_k<float><<<g.grid, g.block, 0, st>>>((const float*)dA, (const float*)z, scale, shift, sums, save_mean, save_invstd, dgamma, dbeta, dbias, (float*)dZ, M, C, m);
     else if (dtype == MNB_BF16) bn_bwd_apply_fused_k<bf16><<<g.grid, g.block, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, sums, save_mean, save_invstd, dgamma, dbeta, dbias, (bf16*)dZ, M, C, m);
@@ -709,7 +711,7 @@ int mnb_bn_bwd_apply_fused(const void* dA, const void* z, const float* scale, co
 int mnb_bn_relu_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y,
                       long long M, int C, int dtype, void* stream) {
     MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_relu_apply: C %% 8 != 0 or M <= 0");
-    ColGeom g = col_geom(M, C, 16);
+    ColGeom g = col_geom(M, C, 16, 8);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MNB_F32) {
         if (residual) bn_relu_apply_k<float, true><<<g.grid, g.block, 0, st>>>((const float*)z, scale, shift, (const float*)residual, (float*)y, M, C);
@@ -726,7 +728,15 @@ int mnb_bn_bwd_reduce(const void* dA, const void* z, const float* scale, const f
                       long long M, int C, int dtype, void* stream) {
     MNB_REQUIRE(C % 8 == 0 && M > 0, "bn_bwd_reduce: C %% 8 != 0 or M <= 0");
     // few, fat CTAs: every CTA ends with one fp64 atomic per channel and same-address atomics serialise in L2
-    ColGeom g = col_geom(M, C, 3);
+    // Every CTA ends with one fp64 atomic per channel, and same-address atomics serialise in L2 (~8 us per CTA-per-SM
+    // on B200, scripts/exp_bn.py): 3 CTAs per SM for the >= 200 MB passes, fewer for the small tensors.
+    int ctas = option_get(OPT_BN_CTAS);
+    if (ctas <= 0) {
+        const double bytes = 2.0 * (double)M * C * (dtype == MNB_F32 ? 4 : 2);
+        ctas = (int)(bytes / (num_sms() * 500.0e3) + 0.5);
+        ctas = ctas < 1 ? 1 : (ctas > 3 ? 3 : ctas);
+    }
+    ColGeom g = col_geom(M, C, ctas);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MNB_F32) bn_bwd_reduce_k<float><<<g.grid, g.block, 0, st>>>((const float*)dA, (const float*)z, scale, shift, sums, M, C);
     else if (dtype == MNB_BF16) bn_bwd_reduce_k<bf16><<<g.grid, g.block, 0, st>>>((const bf16*)dA, (const bf16*)z, scale, shift, sums, M, C);
