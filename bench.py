@@ -221,6 +221,10 @@ def main():
     ap.add_argument("--impl", default="mnb200")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
     ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--height", type=int, default=0, help="rectangular inputs (BASELINE configs[4]): H, with --width")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (BASELINE configs[2]): fixed global batch split over the ranks")
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--ref-batch", type=int, default=32)
@@ -261,12 +265,15 @@ def main():
         ddp.broadcast_parameters(eng)
         sync = ddp.GradSync(eng)
     N, S = args.batch, args.size
+    if args.global_batch:
+        N = args.global_batch // world
+    SH, SW = (args.height or S), (args.width or S)
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     nbuf = 2                                           # alternate two resident batches (each 154 MB > L2)
-    xs = [torch.randn(N, 3, S, S, device=dev, generator=g) for _ in range(nbuf)]
+    xs = [torch.randn(N, 3, SH, SW, device=dev, generator=g) for _ in range(nbuf)]
     ts = [torch.randint(0, 1000, (N,), device=dev, generator=g) for _ in range(nbuf)]
     if args.dump_ops and rank == 0:
-        plan = eng.plan(N, S, S)
+        plan = eng.plan(N, SH, SW)
         seq = []
         for op in plan.fwd:
             seq.append([getattr(op, "label", op.name), getattr(op, "detail", ""), op.name])
@@ -308,66 +315,81 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
     value = world * N * args.steps / (ms / 1e3)
-    launches = eng.launches_per_step(N, S, S) * args.steps
+    scaling = "strong" if args.global_batch else "weak"
+    launches = eng.launches_per_step(N, SH, SW) * args.steps
 
     # ---- end to end through the reference's own loop with pinned host inputs ---------------------------
-    e2e = None
+    # e2e: the loader hands over uint8 HWC batches as decoded (utils/datasets.py:456-462 before ToTensor); ToTensor +
+    # Normalize run inside the stem kernels, so a step ships 1 byte per value.  e2e_fp32_input: the same loop fed the
+    # already-normalised fp32 NCHW tensor exactly as src/train.py:427 does (4 bytes per value).
+    e2e, e2e_f32 = None, None
     if not args.no_e2e:
         crit = torch.nn.CrossEntropyLoss()
         opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-3)
-        hx = [torch.randn(N, 3, S, S).pin_memory() for _ in range(2)]
-        ht = [torch.randint(0, 1000, (N,)).pin_memory() for _ in range(2)]
         copy_stream = torch.cuda.Stream()
 
-        class Prefetch:                                  # the DataLoader side of train.py:423-431
-            def __init__(self):
-                self.i = 0
-                self.nxt = None
-                self.load()
+        def measure(u8):
+            if u8:
+                hx = [torch.randint(0, 256, (N, SH, SW, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            else:
+                hx = [torch.randn(N, 3, SH, SW).pin_memory() for _ in range(2)]
+            ht = [torch.randint(0, 1000, (N,)).pin_memory() for _ in range(2)]
 
-            def load(self):
-                with torch.cuda.stream(copy_stream):
-                    x = hx[self.i % 2].to(dev, non_blocking=True).float()
-                    t = ht[self.i % 2].to(dev, non_blocking=True).long()
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                self.nxt = (x, t, ev)
-                self.i += 1
+            class Prefetch:                              # the DataLoader side of train.py:423-431
+                def __init__(self):
+                    self.i = 0
+                    self.nxt = None
+                    self.load()
 
-            def get(self):
-                x, t, ev = self.nxt
-                torch.cuda.current_stream().wait_event(ev)
-                x.record_stream(torch.cuda.current_stream())
-                t.record_stream(torch.cuda.current_stream())
-                self.load()
-                return x, t
+                def load(self):
+                    with torch.cuda.stream(copy_stream):
+                        x = hx[self.i % 2].to(dev, non_blocking=True)
+                        if not u8:
+                            x = x.float()
+                        t = ht[self.i % 2].to(dev, non_blocking=True).long()
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    self.nxt = (x, t, ev)
+                    self.i += 1
 
-        def loop(k, pf):
-            last = None
-            for _ in range(k):
-                inp, tgt = pf.get()
-                out = model(inp)
-                l = crit(out, tgt)
-                opt.zero_grad()
-                l.backward()                             # DDP: buckets all-reduced + averaged inside backward
-                opt.step()
-                last = l.item()                          # D2H read of the step's loss (train.py:447)
-            return last
-        pf = Prefetch()
-        loop(max(3, args.warmup // 2), pf)
-        barrier()
-        t0 = time.perf_counter()
-        loop(args.steps, pf)
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tm = torch.tensor([dt], device=dev)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dt = float(tm.item())
-        e2e = {"value": world * N * args.steps / dt, "unit": "images/s",
-               "h2d_bytes_per_step": N * 3 * S * S * 4 + N * 8, "d2h_bytes_per_step": 4,
-               "api": "src/train.py:427-440 loop on the drop-in models (model(input), CrossEntropyLoss, "
-                      "zero_grad, backward, torch.optim.Adam.step); pinned host batch prefetched on a copy stream"}
+                def get(self):
+                    x, t, ev = self.nxt
+                    torch.cuda.current_stream().wait_event(ev)
+                    x.record_stream(torch.cuda.current_stream())
+                    t.record_stream(torch.cuda.current_stream())
+                    self.load()
+                    return x, t
+
+            def loop(k, pf):
+                last = None
+                for _ in range(k):
+                    inp, tgt = pf.get()
+                    out = model(inp)
+                    l = crit(out, tgt)
+                    opt.zero_grad()
+                    l.backward()                         # DDP: buckets all-reduced + averaged inside backward
+                    opt.step()
+                    last = l.item()                      # D2H read of the step's loss (train.py:447)
+                return last
+            pf = Prefetch()
+            loop(max(3, args.warmup // 2), pf)
+            barrier()
+            t0 = time.perf_counter()
+            loop(args.steps, pf)
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                tm = torch.tensor([dt], device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dt = float(tm.item())
+            return {"value": world * N * args.steps / dt, "unit": "images/s",
+                    "h2d_bytes_per_step": N * 3 * SH * SW * (1 if u8 else 4) + N * 8, "d2h_bytes_per_step": 4,
+                    "api": "src/train.py:423-440 loop on the drop-in models (model(input), CrossEntropyLoss, zero_grad, "
+                           "backward, torch.optim.Adam.step); pinned host batch prefetched on a copy stream; input "
+                           + ("uint8 N x H x W x 3, ToTensor + Normalize fused into the stem kernels" if u8 else
+                              "fp32 N x 3 x H x W, already normalised (train.py:427)")}
+        e2e = measure(True)
+        e2e_f32 = measure(False)
 
     # ---- roofline pass: per-launch CUDA-event timing of every kernel of the step (rank 0) ----------------
     roof, table = None, None
@@ -396,7 +418,7 @@ def main():
                          "frac_of_hbm_peak": ((v[2] / 1e9) / (v[1] / 1e3)) / hbm if v[1] > 0 else 0.0}
                         for k, v in agg.items()), key=lambda r: -r["ms_per_step"])
         # per family: time of its launches (CUDA events) vs the section-8d algorithmic bytes / flops of its conv calls
-        work = algorithmic_work(eng.plan(N, S, S))
+        work = algorithmic_work(eng.plan(N, SH, SW))
         ncu = None
         try:    # dram__bytes_read+write per kernel class from the committed ncu pass of the same command (profiles/)
             with open(os.path.join(ROOT, "profiles", "r2_ncu_step_summary.json")) as f:
@@ -442,20 +464,21 @@ def main():
 
     cpu, eager = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        eager = gpu_eager_baseline(N, S)
+        eager = gpu_eager_baseline(N, S) if (SH, SW) == (S, S) else None
         cpu = cpu_baseline()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": WORKLOAD if (N, S) == (256, 224) else f"MnasNet {S}x{S} batch {N}/GPU",
+                "config": {"workload": WORKLOAD if (N, SH, SW) == (256, 224, 224) else
+                           f"MnasNet (cut_channels_first=False, head '512') {SH}x{SW} bf16 training, batch {N}/GPU",
                            "global_batch": N * world, "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-3",
                            "dropout": "active", "cuda_graph": bool(use_graph), "gemm_impl": args.gemm,
                            "kernel_options": _kernel_options(),
                            "l2": "no flush needed: each step streams a 154 MB input batch (2 alternating "
                                  "buffers) and ~6 GB of activations, both >> 126 MB L2"},
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "e2e": e2e, "e2e_fp32_input": e2e_f32, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "gpu_eager_baseline": eager, "final_loss": last_loss}
         print(json.dumps(line))
     if world > 1:

@@ -37,6 +37,8 @@ extern "C" {
 
 #define MNB_LAYOUT_NHWC 0
 #define MNB_LAYOUT_NCHW_F32 1   /* network input: N x C x H x W fp32 (train.py:427) */
+#define MNB_LAYOUT_NHWC_U8 2    /* network input: N x H x W x 3 uint8 as decoded (utils/datasets.py:456-462); the stem applies
+                                   ToTensor + Normalize itself: in_scale = mean[3], in_shift = std[3] (classifiers.py:91-92) */
 
 int mnb_version(void);
 /* Kernel-selection switches (process-wide; an unset option takes MNB_<NAME> from the environment, then its default):

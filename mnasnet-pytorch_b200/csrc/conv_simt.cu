@@ -281,9 +281,11 @@ __global__ void __launch_bounds__(256) conv_simt_k(ConvP p) {
 
 // dedicated stem kernels (stem.cu)
 bool stem_supported(int Cin, int Cout, int k, int stride, int pad, int nchw_in);
-int stem_fwd(const float* x, const float* w, const float* bias, void* z, double* stats, int N, int H, int W, int dtype,
+int stem_fwd(const void* x, int x_u8, const float* mean, const float* stdv, const float* w, const float* bias, void* z,
+             double* stats, int N, int H, int W, int dtype,
              cudaStream_t st);
-int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, int dtype, int impl, cudaStream_t st);
+int stem_wgrad(const void* x, int x_u8, const float* mean, const float* stdv, const void* dz, float* dw, int N, int H, int W,
+               int dtype, int impl, cudaStream_t st);
 
 __global__ void pack_weights_k(const float* __restrict__ w, bf16* __restrict__ pf, bf16* __restrict__ pd, int Cout,
                                int Cin, int kk2) {
@@ -300,8 +302,12 @@ static int check_conv(const char* name, int N, int H, int W, int Cin, int Cout, 
                       int x_layout) {
     MNB_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0, "%s: bad N/H/W/Cin", name);
     MNB_REQUIRE(Cout > 0 && Cout % 8 == 0, "%s: Cout=%d must be a positive multiple of 8", name, Cout);
-    MNB_REQUIRE(x_layout == MNB_LAYOUT_NCHW_F32 || Cin % 8 == 0, "%s: Cin=%d must be a multiple of 8 for NHWC input",
+    MNB_REQUIRE(x_layout == MNB_LAYOUT_NHWC || x_layout == MNB_LAYOUT_NCHW_F32 || x_layout == MNB_LAYOUT_NHWC_U8,
+                "%s: bad x_layout %d", name, x_layout);
+    MNB_REQUIRE(x_layout != MNB_LAYOUT_NHWC || Cin % 8 == 0, "%s: Cin=%d must be a multiple of 8 for NHWC input",
                 name, Cin);
+    MNB_REQUIRE(x_layout != MNB_LAYOUT_NHWC_U8 || (Cin == 3 && Cout == 32 && k == 3 && stride == 2 && pad == 1),
+                "%s: uint8 input is lowered for the stem only (3 -> 32, k3 s2 p1)", name);
     MNB_REQUIRE((k == 1 && pad == 0) || (k == 3 && pad == 1), "%s: unsupported k=%d pad=%d", name, k, pad);
     MNB_REQUIRE(stride == 1 || stride == 2, "%s: unsupported stride %d", name, stride);
     MNB_REQUIRE(dtype == MNB_F32 || dtype == MNB_BF16, "%s: bad dtype %d", name, dtype);
@@ -384,8 +390,12 @@ int mnb_conv_fwd_packed(const void* x, const float* in_scale, const float* in_sh
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
     p.nchw_in = x_layout == MNB_LAYOUT_NCHW_F32;
+    if (x_layout == MNB_LAYOUT_NHWC_U8) {       // in_scale / in_shift carry Normalize's mean / std (3 floats each)
+        MNB_REQUIRE(in_scale && in_shift, "conv_fwd: uint8 input needs mean (in_scale) and std (in_shift)");
+        return stem_fwd(x, 1, in_scale, in_shift, w, bias, z, stats, N, H, W, dtype, (cudaStream_t)stream);
+    }
     if (impl != 1 && in_scale == nullptr && stem_supported(Cin, Cout, k, stride, pad, p.nchw_in))
-        return stem_fwd((const float*)x, w, bias, z, stats, N, H, W, dtype, (cudaStream_t)stream);
+        return stem_fwd(x, 0, nullptr, nullptr, w, bias, z, stats, N, H, W, dtype, (cudaStream_t)stream);
     if (dtype == MNB_BF16 && prefer_stream(impl)) {
         int r = conv_fwd_stream(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -451,8 +461,12 @@ int mnb_conv_wgrad(const void* x, const float* in_scale, const float* in_shift, 
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
     p.nchw_in = x_layout == MNB_LAYOUT_NCHW_F32;
+    if (x_layout == MNB_LAYOUT_NHWC_U8) {
+        MNB_REQUIRE(in_scale && in_shift, "conv_wgrad: uint8 input needs mean (in_scale) and std (in_shift)");
+        return stem_wgrad(x, 1, in_scale, in_shift, dz, dw, N, H, W, dtype, impl == 1 ? 2 : impl, (cudaStream_t)stream);
+    }
     if (impl != 1 && in_scale == nullptr && stem_supported(Cin, Cout, k, stride, pad, p.nchw_in))
-        return stem_wgrad((const float*)x, dz, dw, N, H, W, dtype, impl, (cudaStream_t)stream);
+        return stem_wgrad(x, 0, nullptr, nullptr, dz, dw, N, H, W, dtype, impl, (cudaStream_t)stream);
     if (dtype == MNB_BF16 && prefer_stream(impl)) {
         int r = conv_wgrad_stream(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;

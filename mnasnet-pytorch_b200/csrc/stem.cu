@@ -17,13 +17,34 @@ namespace mnb {
 
 constexpr int STEM_CIN = 3, STEM_K = 3, STEM_TAPS = 27;
 
-template <typename T, int COUT>
-__global__ void __launch_bounds__(128) stem_fwd_k(const float* __restrict__ x, const float* __restrict__ w,
+// Network input fetch.  U8 = false: N x 3 x H x W fp32 (src/train.py:427 hands over the normalised tensor).
+// U8 = true: N x H x W x 3 uint8 straight from the decoder -- ToTensor + Normalize(mean, std) of the reference's
+// pipeline (src/utils/datasets.py:456-462, src/models/classifiers.py:91-92) happen HERE, through a 3 x 256 table built
+// per CTA with exactly torch's fp32 operations ((u / 255 - mean) / std), so the result is bit-identical to normalising
+// first and the host-to-device copy carries one byte per value (38.5 MB instead of 154 MB at N = 256).
+template <bool U8>
+__device__ __forceinline__ float stem_in(const void* x, const float* lut, long long n, int ci, int ih, int iw, int H, int W) {
+    if (U8) return lut[ci * 256 + static_cast<const unsigned char*>(x)[((n * H + ih) * W + iw) * STEM_CIN + ci]];
+    return static_cast<const float*>(x)[((n * STEM_CIN + ci) * H + ih) * W + iw];
+}
+__device__ __forceinline__ void stem_build_lut(float* lut, const float* mean, const float* stdv) {
+    for (int i = threadIdx.x; i < STEM_CIN * 256; i += blockDim.x) {
+        const int c = i >> 8;
+        const float v = (float)(i & 255) / 255.f;
+        lut[i] = (v - mean[c]) / stdv[c];
+    }
+}
+
+template <typename T, int COUT, bool U8>
+__global__ void __launch_bounds__(128) stem_fwd_k(const void* __restrict__ x, const float* __restrict__ mean,
+                                                  const float* __restrict__ stdv, const float* __restrict__ w,
                                                   const float* __restrict__ bias, T* __restrict__ z, double* stats,
                                                   int N, int H, int W, int Ho, int Wo) {
     __shared__ __align__(16) float sw[STEM_TAPS][COUT];      // [tap = ci*9 + kh*3 + kw][co]
     __shared__ float sb[COUT];
     __shared__ float sred[2][COUT];
+    __shared__ float lut[U8 ? STEM_CIN * 256 : 1];
+    if (U8) stem_build_lut(lut, mean, stdv);
     for (int i = threadIdx.x; i < STEM_TAPS * COUT; i += blockDim.x) {
         const int co = i % COUT, tap = i / COUT;
         sw[tap][co] = w[co * STEM_TAPS + tap];                // torch layout [co][ci][kh][kw]
@@ -46,7 +67,7 @@ __global__ void __launch_bounds__(128) stem_fwd_k(const float* __restrict__ x, c
                 for (int kw = 0; kw < 3; ++kw) {
                     const int ih = ho * 2 - 1 + kh, iw = wo * 2 - 1 + kw;
                     const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-                    in[ci * 9 + kh * 3 + kw] = ok ? x[(((long long)n * STEM_CIN + ci) * H + ih) * W + iw] : 0.f;
+                    in[ci * 9 + kh * 3 + kw] = ok ? stem_in<U8>(x, lut, n, ci, ih, iw, H, W) : 0.f;
                 }
         float acc[COUT];
 #pragma unroll
@@ -98,11 +119,14 @@ __global__ void __launch_bounds__(128) stem_fwd_k(const float* __restrict__ x, c
 }
 
 // dw[co][tap] += sum_pix dz[pix][co] * xpatch[pix][tap]
-template <typename T, int COUT>
-__global__ void __launch_bounds__(256) stem_wgrad_k(const float* __restrict__ x, const T* __restrict__ dz,
+template <typename T, int COUT, bool U8>
+__global__ void __launch_bounds__(256) stem_wgrad_k(const void* __restrict__ x, const float* __restrict__ mean,
+                                                    const float* __restrict__ stdv, const T* __restrict__ dz,
                                                     float* dw, int N, int H, int W, int Ho, int Wo) {
     constexpr int CG = COUT / 4;                       // channel groups of 4 (8 for Cout = 32)
     __shared__ float sred[COUT * STEM_TAPS];
+    __shared__ float lut[U8 ? STEM_CIN * 256 : 1];
+    if (U8) stem_build_lut(lut, mean, stdv);
     for (int i = threadIdx.x; i < COUT * STEM_TAPS; i += blockDim.x) sred[i] = 0.f;
     __syncthreads();
     const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
@@ -123,7 +147,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_k(const float* __restrict__ x,
                 for (int kw = 0; kw < 3; ++kw) {
                     const int ih = ho * 2 - 1 + kh, iw = wo * 2 - 1 + kw;
                     const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-                    const float v = ok ? x[(((long long)n * STEM_CIN + ci) * H + ih) * W + iw] : 0.f;
+                    const float v = ok ? stem_in<U8>(x, lut, n, ci, ih, iw, H, W) : 0.f;
                     const int t = ci * 9 + kh * 3 + kw;
                     acc[t][0] = fmaf(v, g0, acc[t][0]);
                     acc[t][1] = fmaf(v, g1, acc[t][1]);
@@ -159,13 +183,17 @@ __device__ __forceinline__ void stem_ldmatrix_x4_trans(uint32_t (&r)[4], const v
                  : "r"(addr));
 }
 
-__global__ void __launch_bounds__(128, 4) stem_wgrad_mma_k(const float* __restrict__ x, const bf16* __restrict__ dz,
+template <bool U8>
+__global__ void __launch_bounds__(128, 4) stem_wgrad_mma_k(const void* __restrict__ x, const float* __restrict__ mean,
+                                                           const float* __restrict__ stdv, const bf16* __restrict__ dz,
                                                            float* dw, int N, int H, int W, int Ho, int Wo) {
     constexpr int WARPS = 4, PITCH = 80;                 // 64 bytes of payload per staged row, pitch = 5 x 16 bytes
     constexpr int SEGS = 5;                              // (ci,kh) segments of 3 taps per lane: lanes 0-15 take 0-4, 16-31 take 5-8
     __shared__ __align__(16) unsigned char s_z[WARPS][16 * PITCH];
     __shared__ __align__(16) unsigned char s_p[WARPS][16 * PITCH];
     __shared__ float s_dw[32 * 32];
+    __shared__ float lut[U8 ? STEM_CIN * 256 : 1];
+    if (U8) stem_build_lut(lut, mean, stdv);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_dw[i] = 0.f;
@@ -203,11 +231,10 @@ __global__ void __launch_bounds__(128, 4) stem_wgrad_mma_k(const float* __restri
             const int ci = seg / 3, kh = seg - 3 * ci;
             const int ih = 2 * ho - 1 + kh;
             const bool rok = pok && seg < 9 && ih >= 0 && ih < H;
-            const float* xp = x + (((long long)n * STEM_CIN + ci) * H + ih) * W + iw0;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
                 const int iw = iw0 + kw;
-                xr[i][kw] = (rok && iw >= 0 && iw < W) ? __ldg(xp + kw) : 0.f;
+                xr[i][kw] = (rok && iw >= 0 && iw < W) ? stem_in<U8>(x, lut, n, ci, ih, iw, H, W) : 0.f;
             }
         }
     };
@@ -279,20 +306,28 @@ bool stem_supported(int Cin, int Cout, int k, int stride, int pad, int nchw_in) 
     return nchw_in && Cin == 3 && Cout == 32 && k == 3 && stride == 2 && pad == 1;
 }
 
-int stem_fwd(const float* x, const float* w, const float* bias, void* z, double* stats, int N, int H, int W, int dtype,
-             cudaStream_t st) {
+// x_u8: the input is N x H x W x 3 uint8 and mean / stdv (3 floats each) are the Normalize constants
+int stem_fwd(const void* x, int x_u8, const float* mean, const float* stdv, const float* w, const float* bias, void* z,
+             double* stats, int N, int H, int W, int dtype, cudaStream_t st) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)N * Ho * Wo;
     long long blocks = cdiv(total, 128);
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    if (dtype == MNB_F32) stem_fwd_k<float, 32><<<(unsigned)blocks, 128, 0, st>>>(x, w, bias, (float*)z, stats, N, H, W, Ho, Wo);
-    else stem_fwd_k<bf16, 32><<<(unsigned)blocks, 128, 0, st>>>(x, w, bias, (bf16*)z, stats, N, H, W, Ho, Wo);
+    const unsigned b = (unsigned)blocks;
+    if (dtype == MNB_F32) {
+        if (x_u8) stem_fwd_k<float, 32, true><<<b, 128, 0, st>>>(x, mean, stdv, w, bias, (float*)z, stats, N, H, W, Ho, Wo);
+        else stem_fwd_k<float, 32, false><<<b, 128, 0, st>>>(x, mean, stdv, w, bias, (float*)z, stats, N, H, W, Ho, Wo);
+    } else {
+        if (x_u8) stem_fwd_k<bf16, 32, true><<<b, 128, 0, st>>>(x, mean, stdv, w, bias, (bf16*)z, stats, N, H, W, Ho, Wo);
+        else stem_fwd_k<bf16, 32, false><<<b, 128, 0, st>>>(x, mean, stdv, w, bias, (bf16*)z, stats, N, H, W, Ho, Wo);
+    }
     MNB_LAUNCH_CHECK("stem_fwd");
     return 0;
 }
 
-int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, int dtype, int impl, cudaStream_t st) {
+int stem_wgrad(const void* x, int x_u8, const float* mean, const float* stdv, const void* dz, float* dw, int N, int H, int W,
+               int dtype, int impl, cudaStream_t st) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)N * Ho * Wo;
     long long blocks = cdiv(total, 32);
@@ -302,12 +337,19 @@ int stem_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, i
     // kernel or the "stem_mma" option / MNB_STEM_MMA is 0
     const int use_mma = option_get(OPT_STEM_MMA);
     if (dtype == MNB_BF16 && (impl == 3 || (impl == 0 && use_mma)) && total < (1ll << 31) - 64) {
-        stem_wgrad_mma_k<<<num_sms() * 4, 128, 0, st>>>(x, (const bf16*)dz, dw, N, H, W, Ho, Wo);
+        if (x_u8) stem_wgrad_mma_k<true><<<num_sms() * 4, 128, 0, st>>>(x, mean, stdv, (const bf16*)dz, dw, N, H, W, Ho, Wo);
+        else stem_wgrad_mma_k<false><<<num_sms() * 4, 128, 0, st>>>(x, mean, stdv, (const bf16*)dz, dw, N, H, W, Ho, Wo);
         MNB_LAUNCH_CHECK("stem_wgrad(mma)");
         return 0;
     }
-    if (dtype == MNB_F32) stem_wgrad_k<float, 32><<<(unsigned)blocks, 256, 0, st>>>(x, (const float*)dz, dw, N, H, W, Ho, Wo);
-    else stem_wgrad_k<bf16, 32><<<(unsigned)blocks, 256, 0, st>>>(x, (const bf16*)dz, dw, N, H, W, Ho, Wo);
+    const unsigned b = (unsigned)blocks;
+    if (dtype == MNB_F32) {
+        if (x_u8) stem_wgrad_k<float, 32, true><<<b, 256, 0, st>>>(x, mean, stdv, (const float*)dz, dw, N, H, W, Ho, Wo);
+        else stem_wgrad_k<float, 32, false><<<b, 256, 0, st>>>(x, mean, stdv, (const float*)dz, dw, N, H, W, Ho, Wo);
+    } else {
+        if (x_u8) stem_wgrad_k<bf16, 32, true><<<b, 256, 0, st>>>(x, mean, stdv, (const bf16*)dz, dw, N, H, W, Ho, Wo);
+        else stem_wgrad_k<bf16, 32, false><<<b, 256, 0, st>>>(x, mean, stdv, (const bf16*)dz, dw, N, H, W, Ho, Wo);
+    }
     MNB_LAUNCH_CHECK("stem_wgrad");
     return 0;
 }

@@ -11,7 +11,7 @@ HEADER = os.path.join(ROOT, "include", "mnb200.h")
 LIB_PATH = os.path.join(HERE, "libmnb200.so")
 
 MNB_F32, MNB_BF16 = 0, 1
-LAYOUT_NHWC, LAYOUT_NCHW_F32 = 0, 1
+LAYOUT_NHWC, LAYOUT_NCHW_F32, LAYOUT_NHWC_U8 = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 
 _SCALARS = {

@@ -175,14 +175,15 @@ class _ConvApp:
     """One application of a ConvBlock inside a plan."""
     __slots__ = ("cb", "inp", "z", "stats", "sums", "scale", "shift", "mean", "invstd", "coef", "kind",
                  "Ho", "Wo", "Cout", "k", "stride", "pad", "need_dgrad", "m", "in_bytes", "out_bytes", "label",
-                 "index", "reduce_fused")
+                 "index", "reduce_fused", "in_layout", "in_sc", "in_sh")
 
 
 class Plan:
     """Static program for one input shape (N,H,W): buffers + forward/backward op lists."""
 
-    def __init__(self, eng: "Engine", N: int, H: int, W: int):
+    def __init__(self, eng: "Engine", N: int, H: int, W: int, input_u8: bool = False):
         self.eng, self.N, self.H, self.W = eng, N, H, W
+        self.input_u8 = input_u8     # network input is N x H x W x 3 uint8: the stem normalises it (SURVEY 8f n4)
         self.dev = eng.device
         self.code, self.tdtype = DTYPES[eng.dtype]
         self.esize = 4 if eng.dtype == "fp32" else 2
@@ -311,9 +312,15 @@ class Plan:
         a.need_dgrad = not ref.nchw        # the stem reads the network input: no data gradient
         eng = self.eng
         x_t = ref.t if not ref.nchw else _InputPtr(self)
-        layout = _lib.LAYOUT_NCHW_F32 if ref.nchw else _lib.LAYOUT_NHWC
+        layout = _lib.LAYOUT_NHWC
+        in_sc, in_sh = ref.scale, ref.shift
+        if ref.nchw:
+            layout = _lib.LAYOUT_NHWC_U8 if self.input_u8 else _lib.LAYOUT_NCHW_F32
+            if self.input_u8:
+                in_sc, in_sh = eng.norm_constants(cin)       # Normalize(mean, std) happens inside the stem kernels
+        a.in_layout, a.in_sc, a.in_sh = layout, in_sc, in_sh
         es = self.esize
-        in_b = ref.M * cin * (4 if ref.nchw else es)
+        in_b = ref.M * cin * ((1 if self.input_u8 else 4) if ref.nchw else es)
         out_b = int(a.m) * cout * es
         a.in_bytes, a.out_bytes = in_b, out_b
         a.label = f"dw{k}x{k}" if a.kind == "dw" else (f"conv{k}x{k}" if k > 1 else "pw1x1")
@@ -322,7 +329,7 @@ class Plan:
         for ops, train in ((self.fwd, True), (self.fwd_eval, False)):
             st = a.stats if train else None
             if a.kind == "dense":
-                self._op(ops, "mnb_conv_fwd_packed", x_t, ref.scale, ref.shift, conv.weight, wpk[0], None, a.z, st,
+                self._op(ops, "mnb_conv_fwd_packed", x_t, in_sc, in_sh, conv.weight, wpk[0], None, a.z, st,
                          ref.N, ref.H, ref.W, cin, cout, k, stride, pad, self.code, layout, eng.impl,
                          nbytes=in_b + out_b, label=a.label + "_fwd")
             else:
@@ -550,14 +557,14 @@ class Plan:
                     free.append(gbuf)
                 r = a.inp
                 x_t = r.t if not r.nchw else _InputPtr(self)
-                layout = _lib.LAYOUT_NCHW_F32 if r.nchw else _lib.LAYOUT_NHWC
+                layout = a.in_layout
                 wg = rg(conv.weight)
                 if side and wg:            # fork: the side stream may start once dZ is complete
                     ev_dz = self._new_event()
                     ops.append(_EventOp("record", ev_dz, 0))
                     ops.append(_EventOp("wait", ev_dz, 1))
                 if wg and a.kind == "dense":
-                    self._op(ops, "mnb_conv_wgrad", x_t, r.scale, r.shift, dz, _G(conv.weight), r.N, r.H, r.W,
+                    self._op(ops, "mnb_conv_wgrad", x_t, a.in_sc, a.in_sh, dz, _G(conv.weight), r.N, r.H, r.W,
                              r.C, C, a.k, a.stride, a.pad, self.code, layout, eng.impl,
                              nbytes=a.in_bytes + a.out_bytes, label=a.label + "_wgrad")
                 elif wg:
@@ -837,13 +844,25 @@ class Engine:
     def host_step(self, value: int):
         self.dev_step.fill_(int(value))
 
-    def plan(self, N, H, W) -> Plan:
-        key = (N, H, W, self.store.trainable_sig())
+    def plan(self, N, H, W, input_u8: bool = False) -> Plan:
+        key = (N, H, W, self.store.trainable_sig(), bool(input_u8))
         p = self.plans.get(key)
         if p is None:
-            p = Plan(self, N, H, W)
+            p = Plan(self, N, H, W, bool(input_u8))
             self.plans[key] = p
         return p
+
+    def norm_constants(self, C=3):
+        """Normalize(mean, std) of the input pipeline (module.mean / .std, classifiers.py:91-92) as device vectors."""
+        if getattr(self, "_norm", None) is None:
+            mean = getattr(self.module, "mean", (0.0,) * C)
+            std = getattr(self.module, "std", (1.0,) * C)
+            self._norm = (torch.tensor(mean, device=self.device, dtype=torch.float32),
+                          torch.tensor(std, device=self.device, dtype=torch.float32), {})
+        mean, std, _ = self._norm
+        if mean.numel() != C:
+            raise ValueError(f"{C} input channels, but module.mean has {mean.numel()}")
+        return mean, std
 
     def _check_store(self):
         if not self.store.valid():
@@ -860,9 +879,17 @@ class Engine:
             raise ValueError("expected N x C x H x W input")
         if not x.is_cuda:
             raise RuntimeError("mnb200: input must be a CUDA tensor (no CPU fallback)")
-        x = x.contiguous().float()
-        N, C, H, W = x.shape
-        plan = self.plan(N, H, W)
+        u8 = x.dtype == torch.uint8
+        if u8:
+            # N x H x W x 3 uint8 as decoded: ToTensor + Normalize are fused into the stem (whole-network engines only)
+            if getattr(self.module, "_mnb", None) != "net" or x.shape[-1] != self.in_channels:
+                raise ValueError("uint8 input: expected N x H x W x 3 on a FineTuneModelPool engine")
+            x = x.contiguous()
+            N, H, W, C = x.shape
+        else:
+            x = x.contiguous().float()
+            N, C, H, W = x.shape
+        plan = self.plan(N, H, W, u8)
         stream = torch.cuda.current_stream().cuda_stream
         plan.cur_input = x
         plan.cur_input_ptr = x.data_ptr()
@@ -926,14 +953,8 @@ class Engine:
             raise ValueError("expected a uint8 N x H x W x C tensor")
         x_u8 = x_u8.to(self.device, non_blocking=True).contiguous()
         N, H, W, C = x_u8.shape
-        if getattr(self, "_norm", None) is None:
-            mean = getattr(self.module, "mean", (0.0,) * C)
-            std = getattr(self.module, "std", (1.0,) * C)
-            self._norm = (torch.tensor(mean, device=self.device, dtype=torch.float32),
-                          torch.tensor(std, device=self.device, dtype=torch.float32), {})
-        mean, std, bufs = self._norm
-        if mean.numel() != C:
-            raise ValueError(f"{C} channels, but module.mean has {mean.numel()}")
+        mean, std = self.norm_constants(C)
+        bufs = self._norm[2]
         y = bufs.get((N, H, W))
         if y is None:
             y = bufs[(N, H, W)] = torch.empty((N, C, H, W), device=self.device, dtype=torch.float32)
@@ -990,13 +1011,17 @@ class Engine:
         if self.grad_hook is not None:
             raise RuntimeError("graph replay is single-GPU; use train_step with GradSync for data parallel")
         self._check_store()
-        N, C, H, W = x.shape
-        key = (N, H, W, self.store.trainable_sig(), self.optimizer, self.dropout)
+        u8 = x.dtype == torch.uint8                     # N x H x W x 3 uint8: normalised inside the stem
+        if u8:
+            N, H, W, C = x.shape
+        else:
+            N, C, H, W = x.shape
+        key = (N, H, W, self.store.trainable_sig(), self.optimizer, self.dropout, u8)
         g = self.graphs.get(key)
         if g is None:
-            plan = self.plan(N, H, W)
+            plan = self.plan(N, H, W, u8)
             self.store.adam_state()
-            sx = torch.empty((N, C, H, W), device=self.device, dtype=torch.float32)
+            sx = torch.empty(tuple(x.shape), device=self.device, dtype=torch.uint8 if u8 else torch.float32)
             st = torch.zeros(N, device=self.device, dtype=torch.long)
             sx.copy_(x)
             st.copy_(target)

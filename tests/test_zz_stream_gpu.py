@@ -288,3 +288,50 @@ def test_uint8_input_pipeline_matches_totensor_normalize():
     torch.testing.assert_close(y.cpu(), ref, rtol=1e-6, atol=1e-6)
     out = m(y)                                      # feeds the step like any fp32 NCHW batch
     assert out.shape == (3, 1000) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_uint8_input_fused_into_the_stem(dtype):
+    """model(uint8 N x H x W x 3) -- ToTensor + Normalize(model.mean, model.std) run INSIDE the stem
+    kernels (forward and backward-weight) through a per-CTA table built with torch's own fp32 operations, so logits and
+    every gradient equal the normalise-first path bit for bit up to the atomics' order, and the host-to-device copy of
+    a batch carries one byte per value (src/utils/datasets.py:456-462, src/models/classifiers.py:91-92, train.py:427)."""
+    from mnb200 import engine
+    from oracle import mnasnet_oracle as O
+    g = torch.Generator().manual_seed(0)
+    x8 = torch.randint(0, 256, (3, 64, 96, 3), generator=g, dtype=torch.uint8)
+    t = torch.randint(0, 1000, (3,), generator=g)
+    m = _build(dtype)
+    eng = engine.engine_for(m)
+    crit = torch.nn.CrossEntropyLoss()
+    y = eng.normalize_u8(x8).clone()                # reference path: normalise, then the fp32 NCHW stem
+    out_ref = m(y)
+    crit(out_ref, t.cuda()).backward()
+    z_ref = eng.plan(3, 64, 96).apps[0].z.clone()   # the stem's raw output
+    g_ref = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    out_u8 = m(x8.cuda())                           # fused path: uint8 straight into the stem
+    crit(out_u8, t.cuda()).backward()
+    torch.cuda.synchronize()
+    plan = eng.plan(3, 64, 96, True)
+    assert plan.input_u8 and plan.apps[0].in_bytes == 3 * 64 * 96 * 3
+    assert torch.equal(plan.apps[0].z, z_ref)       # same fp32 arithmetic per element: the stem output is bit-identical
+    # the logits then differ only by run-to-run noise (order of the BN atomics; bf16 amplifies it, SURVEY F9)
+    assert rel(out_u8, out_ref) < (1e-4 if dtype == "fp32" else 0.15)
+    for k, p in m.named_parameters():
+        if k.startswith("classifier") or k == "features.0.conv.weight":
+            assert rel(p.grad, g_ref[k]) < (1e-3 if dtype == "fp32" else 0.3), k
+    # and against the CPU oracle on the torch-normalised input (fp32): the whole uint8 path is the reference's
+    if dtype == "fp32":
+        mean = torch.tensor(m.mean)[None, :, None, None]
+        std = torch.tensor(m.std)[None, :, None, None]
+        xn = (x8.permute(0, 3, 1, 2).float().div(255) - mean) / std
+        torch.manual_seed(42)
+        sd = O.init_state_dict()
+        with torch.no_grad():
+            ref = O.forward(sd, xn, True, dropout_masks="off")
+        assert rel(out_u8, ref) < 1e-4
+    # fused step + graph replay take uint8 batches too
+    l1 = eng.train_step(x8.cuda(), t.cuda(), lr=1e-3).item()
+    l2 = eng.train_step_graph(x8.cuda(), t.cuda(), lr=1e-3).item()
+    assert math.isfinite(l1) and math.isfinite(l2) and l2 < l1 + 0.5
