@@ -119,6 +119,16 @@ int mnb_dw_bwd_fused(const void* dA, const void* z, const float* scale, const fl
                      const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* dbias,
                      const void* x, const float* in_scale, const float* in_shift, const float* w, void* dx, float* dw,
                      double* in_sums, int N, int H, int W, int C, int k, double m, int dtype, void* stream);
+/* Fused backward of one pointwise (1x1) ConvBlock (bf16; csrc/pw_bwd_fused.cu), same contract as mnb_dw_bwd_fused with
+ * the tensors seen as matrices: dA, z are M x Cout; x, dx (and the optional residual skip gradient `add`, summed into
+ * dx) are M x Cin; w, dw are [Cout][Cin] (torch [Cout,Cin,1,1]).  Instantiated for the expand / project blocks of the
+ * 112x112 and 56x56 stages (Cin -> Cout in {16->48, 48->16, 32->16, 24->72, 72->24}; src/models/mnasnet.py:116-129,
+ * 82-85); other shapes return MNB_ERR_UNSUPPORTED and the caller keeps the unfused chain. */
+int mnb_pw_bwd_fused(const void* dA, const void* z, const float* scale, const float* shift, const double* sums,
+                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* dbias,
+                     const void* x, const float* in_scale, const float* in_shift, const float* w, const void* add,
+                     void* dx, float* dw, double* in_sums, long long M, int Cin, int Cout, double m, int dtype,
+                     void* stream);
 
 /* ---- BatchNorm2d (train) : mnasnet.py:55,60 ; torch:nn/modules/batchnorm.py:163-178 ----------------------
  * finalize: mean/var from stats over m positions -> scale = gamma/sqrt(var+eps), shift = beta-mean*scale,
@@ -162,6 +172,12 @@ int mnb_bn_bwd_apply(const void* dA, const void* z, const float* scale, const fl
 /* f[n,c] = mean_hw max(scale*z+shift,0)  (fp32 out)  : AdaptiveAvgPool2d(1) fused with the last BN+ReLU */
 int mnb_gap_fwd(const void* z, const float* scale, const float* shift, float* f, int N, int HW, int C,
                 int dtype, void* stream);
+/* Global average pooling fused with the first Linear of the head (classifiers.py:107-111: pooling -> view -> Dropout ->
+ * Linear): xb[n,c] = bf16( dropout( mean_hw max(scale*z+shift,0) ) ) is the A operand of the tcgen05 FC GEMM
+ * (mnb_fc_fwd_tc), written straight from the pooling reduction; mask (N x C keep flags, NULL = no dropout) and
+ * mask_scale = 1/(1-p) as in mnb_fc_prep_bf16.  f (fp32 pooled features) is optional (NULL = not wanted). */
+int mnb_gap_fc_prep(const void* z, const float* scale, const float* shift, float* f, const unsigned char* mask,
+                    float mask_scale, void* xb, int N, int HW, int C, int dtype, void* stream);
 /* dA[n,hw,c] = df[n,c]/HW */
 int mnb_gap_bwd(const float* df, void* dA, int N, int HW, int C, int dtype, void* stream);
 /* Bernoulli keep-mask (1 = keep) with prob 1-p from a counter-based RNG (seed, offset) : nn.Dropout.

@@ -301,6 +301,10 @@ int dw_fwd_mma(const void* x, const float* s, const float* t, const float* w, co
 int dw_dgrad_mma(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
 int dw_wgrad_mma(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C, int k,
                  cudaStream_t st);
+int pw_bwd_fused(const void* G, const void* Z, const float* scale, const float* shift, const double* sums, const float* mean,
+                 const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
+                 const float* in_scale, const float* in_shift, const float* w, const void* add, void* dX, float* dw,
+                 double* nsums, long long M, int Cin, int Cout, cudaStream_t st);
 int dw_bwd_mma(const void* G, const void* Z, const float* scale, const float* shift, const double* sums, const float* mean,
                const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
                const float* in_scale, const float* in_shift, const float* w, void* dX, float* dw, double* nsums, int N, int H,
@@ -410,6 +414,21 @@ int mnb_dw_bwd_fused(const void* dA, const void* z, const float* scale, const fl
     if (dtype != MNB_BF16) { set_error("dw_bwd_fused: bf16 only"); return MNB_ERR_UNSUPPORTED; }
     return dw_bwd_mma(dA, z, scale, shift, sums, save_mean, save_invstd, m, dgamma, dbeta, dbias, x, in_scale, in_shift, w,
                       dx, dw, in_sums, N, H, W, C, k, (cudaStream_t)stream);
+}
+
+int mnb_pw_bwd_fused(const void* dA, const void* z, const float* scale, const float* shift, const double* sums,
+                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* dbias,
+                     const void* x, const float* in_scale, const float* in_shift, const float* w, const void* add,
+                     void* dx, float* dw, double* in_sums, long long M, int Cin, int Cout, double m, int dtype,
+                     void* stream) {
+    MNB_REQUIRE(M > 0 && Cin > 0 && Cout > 0 && Cin % 8 == 0 && Cout % 8 == 0, "pw_bwd_fused: bad M / Cin / Cout");
+    MNB_REQUIRE(dA && z && scale && shift && sums && save_mean && save_invstd && x && w && dx, "pw_bwd_fused: NULL operand");
+    MNB_REQUIRE(!in_sums || in_scale, "pw_bwd_fused: in_sums needs in_scale / in_shift");
+    MNB_REQUIRE(!in_scale || in_shift, "pw_bwd_fused: in_scale without in_shift");
+    MNB_REQUIRE(m > 0, "pw_bwd_fused: bad element count");
+    if (dtype != MNB_BF16) { set_error("pw_bwd_fused: bf16 only"); return MNB_ERR_UNSUPPORTED; }
+    return pw_bwd_fused(dA, z, scale, shift, sums, save_mean, save_invstd, m, dgamma, dbeta, dbias, x, in_scale, in_shift, w,
+                        add, dx, dw, in_sums, M, Cin, Cout, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fused_k(const T* __restrict_
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void gap_fwd_k(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                          float* __restrict__ f, int N, int HW, int cv) {
+                          float* __restrict__ f, const unsigned char* __restrict__ mask, float ms, bf16* __restrict__ xb,
+                          int N, int HW, int cv) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * cv) return;
     int n = idx / cv, c0 = (idx % cv) * 8;
@@ -344,7 +345,14 @@ __global__ void gap_fwd_k(const T* __restrict__ z, const float* __restrict__ sca
     float inv = 1.f / (float)HW;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] *= inv;
-    store8(f + (long long)n * C + c0, acc);
+    if (f) store8(f + (long long)n * C + c0, acc);
+    if (xb) {       // the first Linear's bf16 A operand, dropout applied: pooling feeds the FC GEMM directly
+        if (mask) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = mask[(long long)n * C + c0 + i] ? acc[i] * ms : 0.f;
+        }
+        store8(xb + (long long)n * C + c0, acc);
+    }
 }
 
 template <typename T>
@@ -771,10 +779,22 @@ int mnb_gap_fwd(const void* z, const float* scale, const float* shift, float* f,
     MNB_REQUIRE(C % 8 == 0 && N > 0 && HW > 0, "gap_fwd: bad shape");
     int total = N * (C / 8);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MNB_F32) gap_fwd_k<float><<<(total + 127) / 128, 128, 0, st>>>((const float*)z, scale, shift, f, N, HW, C / 8);
-    else if (dtype == MNB_BF16) gap_fwd_k<bf16><<<(total + 127) / 128, 128, 0, st>>>((const bf16*)z, scale, shift, f, N, HW, C / 8);
+    if (dtype == MNB_F32) gap_fwd_k<float><<<(total + 127) / 128, 128, 0, st>>>((const float*)z, scale, shift, f, nullptr, 1.f, nullptr, N, HW, C / 8);
+    else if (dtype == MNB_BF16) gap_fwd_k<bf16><<<(total + 127) / 128, 128, 0, st>>>((const bf16*)z, scale, shift, f, nullptr, 1.f, nullptr, N, HW, C / 8);
     else MNB_REQUIRE(false, "gap_fwd: bad dtype");
     MNB_LAUNCH_CHECK("gap_fwd");
+    return 0;
+}
+
+int mnb_gap_fc_prep(const void* z, const float* scale, const float* shift, float* f, const unsigned char* mask,
+                    float mask_scale, void* xb, int N, int HW, int C, int dtype, void* stream) {
+    MNB_REQUIRE(C % 8 == 0 && N > 0 && HW > 0 && xb, "gap_fc_prep: bad shape / NULL operand");
+    int total = N * (C / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_F32) gap_fwd_k<float><<<(total + 127) / 128, 128, 0, st>>>((const float*)z, scale, shift, f, mask, mask_scale, (bf16*)xb, N, HW, C / 8);
+    else if (dtype == MNB_BF16) gap_fwd_k<bf16><<<(total + 127) / 128, 128, 0, st>>>((const bf16*)z, scale, shift, f, mask, mask_scale, (bf16*)xb, N, HW, C / 8);
+    else MNB_REQUIRE(false, "gap_fc_prep: bad dtype");
+    MNB_LAUNCH_CHECK("gap_fc_prep");
     return 0;
 }
 

@@ -369,9 +369,15 @@ class Plan:
         N, C = ref.N, ref.C
         self.head_in = ref
         self.f = self._f32(N, C)
-        for ops in (self.fwd, self.fwd_eval):
-            self._op(ops, "mnb_gap_fwd", ref.t, ref.scale, ref.shift, self.f, N, ref.H * ref.W, C, self.code)
         children = list(mod.classifier)
+        # bf16 + tensor-pipe head: the pooling kernel writes the first Linear's bf16 operand itself (dropout applied),
+        # so GAP feeds the FC GEMM without a pass in between; otherwise a plain pooling kernel
+        lin0 = next((ch for ch in children if isinstance(ch, nn.Linear)), None)
+        gap_fused = (self.eng.dtype == "bf16" and self.eng.impl != 1 and lin0 is not None and C % 8 == 0 and
+                     lin0.out_features % 8 == 0)
+        if not gap_fused:
+            for ops in (self.fwd, self.fwd_eval):
+                self._op(ops, "mnb_gap_fwd", ref.t, ref.scale, ref.shift, self.f, N, ref.H * ref.W, C, self.code)
         cur, width, pending = self.f, C, None
         self.head = []
         self.dropout_masks = []
@@ -407,8 +413,13 @@ class Plan:
                     for ops, train in ((self.fwd, True), (self.fwd_eval, False)):
                         self._op(ops, "mnb_pack_weights", ch.weight, pf, pd if train else None, O, width, 1,
                                  label="pack_weights")
-                        self._op(ops, "mnb_fc_prep_bf16", cur, maskp if train else None, msc if train else 1.0, xb,
-                                 N * width)
+                        if cur is self.f and gap_fused:
+                            self._op(ops, "mnb_gap_fc_prep", ref.t, ref.scale, ref.shift, self.f,
+                                     maskp if train else None, msc if train else 1.0, xb, N, ref.H * ref.W, C,
+                                     self.code, label="gap+fc_prep")
+                        else:
+                            self._op(ops, "mnb_fc_prep_bf16", cur, maskp if train else None, msc if train else 1.0,
+                                     xb, N * width)
                         self._op(ops, "mnb_fc_fwd_tc", xb, ch.weight, pf, ch.bias, y, int(relu), N, width, O,
                                  label="fc_fwd(tcgen05)")
                 else:
@@ -545,6 +556,29 @@ class Plan:
                         free.append(gbuf)
                     gbuf = dx
                     continue
+                if self._fused_pw_backward(a, idx, first_live):
+                    # one kernel: BN-backward elementwise pass + backward-data (+ skip gradient) + backward-weight of
+                    # this 1x1 block + the BN-backward reductions of the block that produced its input
+                    # (csrc/pw_bwd_fused.cu)
+                    r = a.inp
+                    pa = self.apps[a.index - 1] if (a.index > 0 and r.scale is not None and
+                                                    self.apps[a.index - 1].z is r.t) else None
+                    if not a.reduce_fused:
+                        self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
+                                 nbytes=2 * a.out_bytes, label="bn_bwd_reduce")
+                    dx = take()
+                    add = held[-1] if (idx > 0 and self.tape[idx - 1][0] == "res_begin") else None
+                    self._op(ops, "mnb_pw_bwd_fused", gbuf, a.z, a.scale, a.shift, a.sums, a.mean, a.invstd,
+                             Gp(bn.weight), Gp(bn.bias), Gp(conv.bias), r.t, r.scale, r.shift, conv.weight, add, dx,
+                             Gp(conv.weight), pa.sums if pa is not None else None, r.M, r.C, C, a.m, self.code,
+                             nbytes=2 * a.out_bytes + a.in_bytes * (3 if add is not None else 2),
+                             label=a.label + "_bwd_fused")
+                    if pa is not None:
+                        pa.reduce_fused = True
+                    if not any(gbuf is h for h in held):
+                        free.append(gbuf)
+                    gbuf = dx
+                    continue
                 dz = take()
                 if not a.reduce_fused:     # else: done in the epilogue of the dgrad that produced gbuf
                     self._op(ops, "mnb_bn_bwd_reduce", gbuf, a.z, a.scale, a.shift, a.sums, M, C, self.code,
@@ -622,6 +656,18 @@ class Plan:
         if eng.fuse_dw_bwd == 2:                 # forced (tests): every shape the kernel supports
             return r.H >= 1
         return a.k == 3 and r.H >= 56 and r.W >= 24 and a.Cout % 24 == 0
+
+    PW_FUSED_SHAPES = {(16, 48), (48, 16), (32, 16), (24, 72), (72, 24)}       # (Cin, Cout) instantiated in pw_bwd_fused.cu
+
+    def _fused_pw_backward(self, a, idx, first_live) -> bool:
+        """Where the fused pointwise backward kernel is used: bf16 1x1 blocks of the shapes it is instantiated for (the
+        expand / project blocks of the 112x112 and 56x56 stages), whose data gradient is needed."""
+        eng = self.eng
+        if eng.dtype != "bf16" or not eng.fuse_pw_bwd or a.kind != "dense" or a.k != 1 or a.stride != 1:
+            return False
+        if a.inp.nchw or not (a.need_dgrad and idx > first_live):
+            return False
+        return (a.inp.C, a.Cout) in self.PW_FUSED_SHAPES
 
     def _new_event(self):
         self.n_events += 1
@@ -831,6 +877,7 @@ class Engine:
         self.fuse_bn_reduce = False    # BN-backward reductions in the producing dgrad epilogue (tested; off:
                                        # the dgrad epilogues are the bottleneck, the separate kernel is faster)
         self.fuse_dw_bwd = 1           # fused depthwise ConvBlock backward (csrc/dw_mma.cu): 0 off, 1 where it wins, 2 always
+        self.fuse_pw_bwd = 1           # fused pointwise ConvBlock backward (csrc/pw_bwd_fused.cu) for its shapes
         self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
         self.optimizer = "adam"        # 'adam' | 'rmsprop' | 'sgd' (train.py:218-231); set before the first graph capture
 

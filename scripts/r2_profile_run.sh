@@ -1,0 +1,27 @@
+#!/bin/bash
+# One gpurun call that refreshes the measured artefacts of the shipped defaults (round 2):
+#   gpurun --timeout 1700 -- 'bash scripts/r2_profile_run.sh'        (everything lands in gpurun_out/)
+set -u
+mkdir -p gpurun_out
+echo "== bench (1 GPU, BASELINE configs[1]) =="
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --profile-out gpurun_out/r2_kernel_table.json > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err; tail -c 300 gpurun_out/r2_bench_1gpu.json
+echo "== reference arm =="
+timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r2_bench_reference_arm.json 2>&1
+echo "== configs[3] progressive 112^2 batch 512, configs[4] 192x256 / 256x192 batch 256, configs[2] strong N=2048 on one GPU =="
+timeout 300 python bench.py --batch 512 --size 112 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_cfg3_112_b512.json 2>&1
+timeout 300 python bench.py --batch 256 --height 192 --width 256 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_cfg4_192x256.json 2>&1
+timeout 300 python bench.py --batch 256 --height 256 --width 192 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_cfg4_256x192.json 2>&1
+timeout 600 python bench.py --global-batch 2048 --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_cfg2_strong_2048_1gpu.json 2>&1
+echo "== ncu launch list of one timed step (shares + DRAM bytes; never a bench value) =="
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    -k 'regex:_k$' --csv --log-file gpurun_out/ncu_raw.csv \
+    python bench.py --steps 1 --warmup 3 --no-graph --no-e2e --no-cpu-baseline --dump-ops gpurun_out/ops.json > gpurun_out/ncu_bench.log 2>&1
+python scripts/ncu_summarize.py gpurun_out/ncu_raw.csv gpurun_out/ops.json r2 gpurun_out > gpurun_out/ncu_summarize.log 2>&1 || tail -3 gpurun_out/ncu_summarize.log
+rm -f gpurun_out/ncu_raw.csv
+echo "== ncu --set full of a few GEMM / depthwise launches of the timed step (tensor-pipe, issue, DRAM); small .ncu-rep =="
+timeout 600 ncu --set full --clock-control none -k 'regex:conv_tc_k|pw_stream_k|pw_wgrad_stream_k|dw_mma|pw_bwd_fused' \
+    --launch-skip 520 --launch-count 40 -o gpurun_out/r2_ncu_step_gemm_dw -f \
+    python bench.py --steps 1 --warmup 3 --no-graph --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
+ls -la gpurun_out/*.ncu-rep
+echo done
