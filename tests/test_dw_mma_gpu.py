@@ -176,6 +176,7 @@ def test_engine_fused_depthwise_backward_matches_unfused(n, h, w):
     m = build("bf16")
     eng = engine.engine_for(m)
     eng.fuse_dw_bwd = 0
+    eng.fuse_pw_bwd = 0                  # (the fused pointwise backward has its own test, tests/test_pw_bwd_gpu.py)
     eng.wgrad_slack = 0                  # single stream: the second program may reuse the first one's scratch
     out = m(x.cuda())
     loss = torch.nn.CrossEntropyLoss()(out, t.cuda())
