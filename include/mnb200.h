@@ -51,6 +51,12 @@ int mnb_version(void);
  *                            2 and 3 are untimed experiments: more memory-level parallelism, more registers)
  *   "dw_stream_tw8" (default 0) 3x3 row-stream forward / backward-data with 8 instead of 4 output columns per lane
  *                            (fewer halo loads and per-row overheads per output, more registers; untimed experiment)
+ *   "dw_mma" (default 1)     bf16 depthwise layers on the TMA + mma.sync kernels (dw_mma.cu): 1 = where they measured
+ *                            faster than the tile kernels (forward / backward-data on maps of >= 12 rows, backward-weight
+ *                            when additionally C % 24 == 0), 2 = every shape, 0 = never
+ *   "dw_mma_cg" / "dw_mma_tws" / "dw_mma_seg" (default 0 = automatic)  geometry overrides of those kernels: channels per
+ *                            CTA (24 | 40), 16-column strips per CTA (1 | 2), row blocks per work item
+ *   "bn_ctas" (default 0 = sized to the tensor)  CTAs per SM of mnb_bn_bwd_reduce
  * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current value or MNB_ERR_ARG. */
 int mnb_set_option(const char* name, int value);
 int mnb_get_option(const char* name);
