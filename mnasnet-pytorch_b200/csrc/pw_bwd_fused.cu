@@ -17,6 +17,8 @@
 //                  the pixel row, is the slow index of both tiles); A_x = relu(s_in*x+t_in) applied to the fragments;
 //                  accumulators stay in registers for the CTA's life
 // and the finished dX rows are staged for the TMA store and reduced against the raw X for the producing block.
+#include <stdlib.h>
+
 #include "dw_mma.cuh"
 
 namespace mnb {
@@ -60,6 +62,7 @@ struct PwbP {
     float* dw;                  // [Cout][Cin] += (NULL = frozen)
     double* nsums;              // [2][Cin] reductions for the producing block (NULL = none)
     int has_add;                // residual skip gradient added into dX
+    int cin_total;              // Cin of the layer; a CTA column (blockIdx.y) owns the CI-channel slice blockIdx.y * CI
     long long M;
 };
 
@@ -99,6 +102,10 @@ __global__ void __launch_bounds__(PwbCfg<CO, CI>::THREADS)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const bool act_in = p.in_scale != nullptr;
     const bool do_red = p.nsums != nullptr && act_in, do_wgrad = p.dw != nullptr;
+    // Input-channel slicing for wide inputs (240 -> 40: five 48-channel slices): backward-data, backward-weight, the
+    // skip add and the producer reductions are all independent per input channel; only the (narrow) G / Z tiles are
+    // re-read by every slice, from L2.
+    const int ci0 = blockIdx.y * CI, CIT = p.cin_total;
 
     if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
     for (int i = tid; i < Cfg::CO_PAD * CI; i += THREADS) dwacc[i] = 0.f;
@@ -111,15 +118,15 @@ __global__ void __launch_bounds__(PwbCfg<CO, CI>::THREADS)
         const double cc = -s * sg / p.m - bb * mean;
         coef[c] = (float)s; coef[CO + c] = (float)bb; coef[2 * CO + c] = (float)cc;
         coef[3 * CO + c] = p.scale[c]; coef[4 * CO + c] = p.shift[c];
-        if (blockIdx.x == 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
             if (p.dgamma) p.dgamma[c] += (float)dga;
             if (p.dbeta) p.dbeta[c] += (float)sg;
             if (p.dbias) p.dbias[c] += (float)(s * sg + bb * mean * p.m + cc * p.m);   // analytically 0
         }
     }
     for (int c = tid; c < CI; c += THREADS) {
-        icoef[c] = act_in ? p.in_scale[c] : 1.f;
-        icoef[CI + c] = act_in ? p.in_shift[c] : 0.f;
+        icoef[c] = act_in ? p.in_scale[ci0 + c] : 1.f;
+        icoef[CI + c] = act_in ? p.in_shift[ci0 + c] : 0.f;
         red[c] = 0.f; red[CI + c] = 0.f;
     }
     // backward-data B fragments: B[k = co][n = ci] = w[co][ci]; register (ks, nt, h) = rows k = 16ks + 8h + 2t, +1 of
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(PwbCfg<CO, CI>::THREADS)
             for (int h = 0; h < 2; ++h) {
                 const int co = 16 * ks + 8 * h + 2 * t, ci = 8 * nt + g;
                 float w0 = 0.f, w1 = 0.f;
-                if (co + 1 < CO) { w0 = p.w[co * CI + ci]; w1 = p.w[(co + 1) * CI + ci]; }
+                if (co + 1 < CO) { w0 = p.w[co * CIT + ci0 + ci]; w1 = p.w[(co + 1) * CIT + ci0 + ci]; }
                 wb[ks][nt][h] = pack_bf16x2(w0, w1);
             }
     // transform mapping: one 8-channel chunk of (G, Z) per thread for life
@@ -165,8 +172,8 @@ __global__ void __launch_bounds__(PwbCfg<CO, CI>::THREADS)
         mbar_expect_tx(bar0 + 8 * b, (uint32_t)(2 * GB + XBB + (p.has_add ? XBB : 0)));
         tma_load4(sb, &tm_g, 0, row0, 0, 0, bar0 + 8 * b);
         tma_load4(sb + GB, &tm_z, 0, row0, 0, 0, bar0 + 8 * b);
-        tma_load4(sb + 2 * GB, &tm_x, 0, row0, 0, 0, bar0 + 8 * b);
-        if (p.has_add) tma_load4(sb + 2 * GB + XBB, &tm_add, 0, row0, 0, 0, bar0 + 8 * b);
+        tma_load4(sb + 2 * GB, &tm_x, ci0, row0, 0, 0, bar0 + 8 * b);
+        if (p.has_add) tma_load4(sb + 2 * GB + XBB, &tm_add, ci0, row0, 0, 0, bar0 + 8 * b);
     };
     long long tile = blockIdx.x;
     if (tid == 0 && tile < ntiles) issue(tile, 0);
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(PwbCfg<CO, CI>::THREADS)
         }
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) tma_store4(&tm_dx, 0, (int)row0, 0, 0, OUT);
+        if (tid == 0) tma_store4(&tm_dx, ci0, (int)row0, 0, 0, OUT);
         b ^= 1;
     }
     if (tid == 0) tma_store_wait_read();
@@ -336,27 +343,30 @@ __global__ void __launch_bounds__(PwbCfg<CO, CI>::THREADS)
     }
     __syncthreads();
     if (do_wgrad)
-        for (int i = tid; i < CO * CI; i += THREADS) atomicAdd(&p.dw[i], dwacc[i]);
+        for (int i = tid; i < CO * CI; i += THREADS) atomicAdd(&p.dw[(i / CI) * CIT + ci0 + i % CI], dwacc[i]);
     if (do_red)
         for (int i = tid; i < CI; i += THREADS) {
-            atomicAdd(&p.nsums[i], (double)red[i]);
-            atomicAdd(&p.nsums[CI + i], (double)red[CI + i]);
+            atomicAdd(&p.nsums[ci0 + i], (double)red[i]);
+            atomicAdd(&p.nsums[CIT + ci0 + i], (double)red[CI + i]);
         }
 }
 
 template <int CO, int CI>
-static int launch_pwb(const PwbP& p, const void* G, const void* Z, const void* X, const void* add, void* dX,
+static int launch_pwb(const PwbP& p0, const void* G, const void* Z, const void* X, const void* add, void* dX, int Cin,
                       cudaStream_t st) {
     using Cfg = PwbCfg<CO, CI>;
+    PwbP p = p0;
+    p.cin_total = Cin;
+    const int slices = Cin / CI;
     const char* name = "pw_bwd_fused";
     if (p.M >= (1ll << 31) - Cfg::R) { set_error("%s: too many rows", name); return MNB_ERR_UNSUPPORTED; }
     const int M = (int)p.M;
     CUtensorMap tm_g, tm_z, tm_x, tm_add, tm_dx;
     if (int e = dwm_tensor_map(&tm_g, G, 1, 1, M, CO, CO, Cfg::R, 1)) return e;
     if (int e = dwm_tensor_map(&tm_z, Z, 1, 1, M, CO, CO, Cfg::R, 1)) return e;
-    if (int e = dwm_tensor_map(&tm_x, X, 1, 1, M, CI, CI, Cfg::R, 1)) return e;
-    if (int e = dwm_tensor_map(&tm_add, add ? add : X, 1, 1, M, CI, CI, Cfg::R, 1)) return e;
-    if (int e = dwm_tensor_map(&tm_dx, dX, 1, 1, M, CI, CI, Cfg::R, 1)) return e;
+    if (int e = dwm_tensor_map(&tm_x, X, 1, 1, M, Cin, CI, Cfg::R, 1)) return e;
+    if (int e = dwm_tensor_map(&tm_add, add ? add : X, 1, 1, M, Cin, CI, Cfg::R, 1)) return e;
+    if (int e = dwm_tensor_map(&tm_dx, dX, 1, 1, M, Cin, CI, Cfg::R, 1)) return e;
     static int occ = -1;
     if (occ < 0) {
         cudaError_t e = cudaFuncSetAttribute(pw_bwd_fused_k<CO, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -367,9 +377,10 @@ static int launch_pwb(const PwbP& p, const void* G, const void* Z, const void* X
         occ = o;
     }
     const long long ntiles = (p.M + Cfg::R - 1) / Cfg::R;
-    long long grid = (long long)num_sms() * occ;
+    long long grid = ((long long)num_sms() * occ + slices - 1) / slices;
     if (grid > ntiles) grid = ntiles;
-    pw_bwd_fused_k<CO, CI><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(tm_g, tm_z, tm_x, tm_add, tm_dx, p);
+    pw_bwd_fused_k<CO, CI><<<dim3((unsigned)grid, (unsigned)slices), Cfg::THREADS, Cfg::SMEM, st>>>(tm_g, tm_z, tm_x, tm_add,
+                                                                                                  tm_dx, p);
     MNB_LAUNCH_CHECK(name);
     return 0;
 }
@@ -382,13 +393,24 @@ int pw_bwd_fused(const void* G, const void* Z, const float* scale, const float* 
     p.scale = scale; p.shift = shift; p.sums = sums; p.mean = mean; p.invstd = invstd; p.m = m;
     p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias; p.in_scale = in_scale; p.in_shift = in_shift; p.w = w; p.dw = dw;
     p.nsums = nsums; p.has_add = add != nullptr; p.M = M;
-#define MNB_PWB(CO_, CI_) if (Cout == CO_ && Cin == CI_) return launch_pwb<CO_, CI_>(p, G, Z, X, add, dX, st)
+#define MNB_PWB(CO_, CI_) if (Cout == CO_ && Cin == CI_) return launch_pwb<CO_, CI_>(p, G, Z, X, add, dX, Cin, st)
     MNB_PWB(48, 16);
     MNB_PWB(16, 48);
     MNB_PWB(16, 32);
     MNB_PWB(72, 24);
-    MNB_PWB(24, 72);
+    if (Cout == 24 && Cin == 72) {
+        static const bool whole = getenv("MNB_PW_NOSLICE72") != nullptr;  // experiment: one 72-channel slice (212 registers)
+        if (whole) return launch_pwb<24, 72>(p, G, Z, X, add, dX, Cin, st);
+        return launch_pwb<24, 24>(p, G, Z, X, add, dX, Cin, st);
+    }
 #undef MNB_PWB
+    // wide-input project blocks: input-channel slices of 48 / 24 (one CTA column per slice)
+    if (Cout == 40 && Cin == 240) {
+        static const bool wide = getenv("MNB_PW_SLICE48") != nullptr;     // experiment: 5 slices of 48 instead of 10 of 24
+        if (wide) return launch_pwb<40, 48>(p, G, Z, X, add, dX, Cin, st);
+        return launch_pwb<40, 24>(p, G, Z, X, add, dX, Cin, st);
+    }
+    if (Cout == 80 && Cin == 480) return launch_pwb<80, 24>(p, G, Z, X, add, dX, Cin, st);
     set_error("pw_bwd_fused: shape %d -> %d not instantiated", Cin, Cout);
     return MNB_ERR_UNSUPPORTED;
 }
