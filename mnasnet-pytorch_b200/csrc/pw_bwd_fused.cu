@@ -17,8 +17,6 @@
 //                  the pixel row, is the slow index of both tiles); A_x = relu(s_in*x+t_in) applied to the fragments;
 //                  accumulators stay in registers for the CTA's life
 // and the finished dX rows are staged for the TMA store and reduced against the raw X for the producing block.
-#include <stdlib.h>
-
 #include "dw_mma.cuh"
 
 namespace mnb {
@@ -398,19 +396,11 @@ int pw_bwd_fused(const void* G, const void* Z, const float* scale, const float* 
     MNB_PWB(16, 48);
     MNB_PWB(16, 32);
     MNB_PWB(72, 24);
-    if (Cout == 24 && Cin == 72) {
-        static const bool whole = getenv("MNB_PW_NOSLICE72") != nullptr;  // experiment: one 72-channel slice (212 registers)
-        if (whole) return launch_pwb<24, 72>(p, G, Z, X, add, dX, Cin, st);
-        return launch_pwb<24, 24>(p, G, Z, X, add, dX, Cin, st);
-    }
+    MNB_PWB(24, 72);
 #undef MNB_PWB
-    // wide-input project blocks: input-channel slices of 48 / 24 (one CTA column per slice)
-    if (Cout == 40 && Cin == 240) {
-        static const bool wide = getenv("MNB_PW_SLICE48") != nullptr;     // experiment: 5 slices of 48 instead of 10 of 24
-        if (wide) return launch_pwb<40, 48>(p, G, Z, X, add, dX, Cin, st);
-        return launch_pwb<40, 24>(p, G, Z, X, add, dX, Cin, st);
-    }
-    if (Cout == 80 && Cin == 480) return launch_pwb<80, 24>(p, G, Z, X, add, dX, Cin, st);
+    // (Input-channel slicing -- launch_pwb<CO, CIS> with Cin / CIS CTA columns -- was measured for 72 -> 24, 240 -> 40 and
+    // 480 -> 80: every slice repeats the dZ transform of the G / Z tile, which is the dominant instruction cost, and it
+    // lost to the unfused chain (272 vs 176 us at 28x28 240 -> 40).  Wide layers need the Cout / Cin split over warps.)
     set_error("pw_bwd_fused: shape %d -> %d not instantiated", Cin, Cout);
     return MNB_ERR_UNSUPPORTED;
 }
