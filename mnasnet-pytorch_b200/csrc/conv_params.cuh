@@ -41,4 +41,9 @@ int conv_fwd_stream(const ConvP& p, cudaStream_t st);
 int conv_dgrad_stream(const ConvP& p, cudaStream_t st);
 int conv_wgrad_stream(const ConvP& p, cudaStream_t st);
 
+// TMA + mma.sync path for the small-channel 3x3 stage transitions (c3_mma.cu); MNB_ERR_UNSUPPORTED otherwise
+int conv_fwd_c3(const ConvP& p, cudaStream_t st);
+int conv_dgrad_c3(const ConvP& p, cudaStream_t st);
+int conv_wgrad_c3(const ConvP& p, cudaStream_t st);
+
 }  // namespace mnb

@@ -400,6 +400,10 @@ int mnb_conv_fwd_packed(const void* x, const float* in_scale, const float* in_sh
         int r = conv_fwd_stream(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
+    if (dtype == MNB_BF16 && (impl == 0 || impl == 3)) {
+        int r = conv_fwd_c3(p, (cudaStream_t)stream);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (impl != 1 && dtype == MNB_BF16) {
         int r = conv_fwd_tc(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
@@ -421,6 +425,10 @@ int mnb_conv_dgrad_packed(const void* dz, const float* w, const void* wpk, const
     p.Ho = (H + 2 * pad - k) / stride + 1; p.Wo = (W + 2 * pad - k) / stride + 1;
     if (dtype == MNB_BF16 && prefer_stream(impl)) {
         int r = conv_dgrad_stream(p, (cudaStream_t)stream);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
+    if (dtype == MNB_BF16 && (impl == 0 || impl == 3)) {
+        int r = conv_dgrad_c3(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
     if (impl != 1 && dtype == MNB_BF16) {
@@ -469,6 +477,10 @@ int mnb_conv_wgrad(const void* x, const float* in_scale, const float* in_shift, 
         return stem_wgrad(x, 0, nullptr, nullptr, dz, dw, N, H, W, dtype, impl, (cudaStream_t)stream);
     if (dtype == MNB_BF16 && prefer_stream(impl)) {
         int r = conv_wgrad_stream(p, (cudaStream_t)stream);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
+    if (dtype == MNB_BF16 && (impl == 0 || impl == 3)) {
+        int r = conv_wgrad_c3(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
     if (impl != 1 && dtype == MNB_BF16) {
