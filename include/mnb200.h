@@ -57,6 +57,8 @@ int mnb_version(void);
  *   "dw_mma_cg" / "dw_mma_tws" / "dw_mma_seg" (default 0 = automatic)  geometry overrides of those kernels: channels per
  *                            CTA (24 | 40), 16-column strips per CTA (1 | 2), row blocks per work item
  *   "bn_ctas" (default 0 = sized to the tensor)  CTAs per SM of mnb_bn_bwd_reduce
+ *   "dw_small"  (default 1)  whole-tile tensor-pipe depthwise kernels (dw_small.cu) for maps of 12..28 rows (forward,
+ *                            backward-data, backward-weight), 2 = every map of at most 28 rows, 0 = never
  *   "c3_mma"    (default 1)  bulk-copy + mma.sync kernels for the stride-2 3x3 stage transitions 16->24, 24->40 (forward,
  *                            backward-data, backward-weight) and 40->80 (backward-data) under impl 0 / 3 (c3_mma.cu)
  * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current value or MNB_ERR_ARG. */

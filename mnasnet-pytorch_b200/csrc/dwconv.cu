@@ -301,6 +301,13 @@ int dw_fwd_mma(const void* x, const float* s, const float* t, const float* w, co
 int dw_dgrad_mma(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
 int dw_wgrad_mma(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C, int k,
                  cudaStream_t st);
+// whole-tile variants for maps of at most 28 rows (dw_small.cu), option "dw_small"
+bool dw_small_covers(int H, int W, int C, int k);
+int dw_fwd_small(const void* x, const float* s, const float* t, const float* w, void* z, double* stats, int N, int H, int W,
+                 int C, int k, cudaStream_t st);
+int dw_dgrad_small(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
+int dw_wgrad_small(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C, int k,
+                   cudaStream_t st);
 int pw_bwd_fused(const void* G, const void* Z, const float* scale, const float* shift, const double* sums, const float* mean,
                  const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
                  const float* in_scale, const float* in_shift, const float* w, const void* add, void* dX, float* dw,
@@ -318,6 +325,10 @@ int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, cons
     if (int e = check_dw("dw_fwd", N, H, W, C, k, dtype)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     // tensor-pipe kernel from 14-row maps up (7x7 / 4x4 maps fill 16-pixel strips too poorly: tile kernel); dw_mma = 2 forces it
+    if (dtype == MNB_BF16 && !bias && dw_small_covers(H, W, C, k)) {
+        int r = dw_fwd_small(x, in_scale, in_shift, w, z, stats, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16 && !bias && !use_dw_stream(0, H, k) &&
         (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12))) {
         int r = dw_fwd_mma(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
@@ -348,6 +359,10 @@ int mnb_dw_dgrad(const void* dz, const float* w, void* dx, const void* bn_z, con
     MNB_REQUIRE(!bn_z || (bn_scale && bn_shift && bn_sums), "dw_dgrad: bn_z needs bn_scale/bn_shift/bn_sums");
     if (!bn_z) bn_sums = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MNB_BF16 && !bn_z && dw_small_covers(H, W, C, k)) {
+        int r = dw_dgrad_small(dz, w, dx, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16 && !bn_z && !use_dw_stream(1, H, k) &&
         (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12))) {
         int r = dw_dgrad_mma(dz, w, dx, N, H, W, C, k, st);
@@ -378,6 +393,10 @@ int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, co
     cudaStream_t st = (cudaStream_t)stream;
     // tensor-pipe backward-weight where it measured faster than the tile kernel (profiles/r2_exp_dw_mma.json): maps of
     // >= 12 rows whose channel count the 24-channel geometry tiles exactly (not the 32-channel stem block)
+    if (dtype == MNB_BF16 && dw_small_covers(H, W, C, k)) {
+        int r = dw_wgrad_small(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     if (dtype == MNB_BF16 && !use_dw_stream(2, H, k) &&
         (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12 && C % 24 == 0))) {
         int r = dw_wgrad_mma(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);

@@ -34,10 +34,12 @@ def rel(a, b):
 @pytest.fixture()
 def forced_mma():
     from mnb200 import _lib as L
-    old = L.get_option("dw_mma")
+    old, old_small = L.get_option("dw_mma"), L.get_option("dw_small")
     L.set_option("dw_mma", 2)           # 2 = every bf16 shape, not only the ones where it is the fastest kernel
+    L.set_option("dw_small", 0)         # the whole-tile kernels (dw_small.cu, tests/test_dw_small_gpu.py) take the small maps otherwise
     yield L
     L.set_option("dw_mma", old)
+    L.set_option("dw_small", old_small)
 
 
 def _operands(N, H, W, C, k, seed=0):
