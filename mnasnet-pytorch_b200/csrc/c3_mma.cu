@@ -25,20 +25,6 @@
 
 namespace mnb {
 
-// ---- 1-D bulk copies (contiguous tiles) ---------------------------------------------------------------------
-__device__ __forceinline__ void bulk_store1(void* gdst, uint32_t ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_load1(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
-                 "l"(gsrc), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void ldsm1(uint32_t addr, uint32_t& r0) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
-}
-
 struct C3P {
     const float* in_scale;      // BN scale / shift of the producing ConvBlock (NULL = plain input)
     const float* in_shift;

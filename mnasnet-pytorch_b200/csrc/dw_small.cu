@@ -348,6 +348,307 @@ __global__ void __launch_bounds__(DwsCfg<K, CG, TWS, TH>::THREADS, DwsCfg<K, CG,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Fused depthwise ConvBlock backward on a whole tile (same contract as dw_mma.cu's dw_mma_bwd_k / mnb_dw_bwd_fused):
+//     dZ = a * G * [scale*Z + shift > 0] + b * Z + c  (in place over the G tile, halo included),
+//     dX = dZ (*) rot180(w)  -> staged over the Z tile, TMA store;  sum(dX'), sum(dX' x) of the producing block;
+//     dW += dZ^T A(X)  on the tile's own rows.
+// G, Z: TR x HC boxes (halo rows / columns: zero outside the image), X: TR x TW box.  Single-buffered: 2-4 CTAs share an SM.
+// ---------------------------------------------------------------------------------------------------------------
+struct DwsBP {
+    const float* scale;         // this block's BN scale / shift (ReLU mask)
+    const float* shift;
+    const double* sums;         // [2][C] sum(G'), sum(G' z) of this block (already reduced)
+    const float* mean;
+    const float* invstd;
+    double m;
+    float* dgamma;              // += (NULL = frozen)
+    float* dbeta;
+    float* dbias;
+    const float* in_scale;      // producing block's BN scale / shift
+    const float* in_shift;
+    const float* w;
+    float* dw;                  // += (NULL = frozen)
+    double* nsums;              // [2][C] sum(dX'), sum(dX' x) for the producing block (NULL = not wanted)
+    int N, H, W, C;
+    int tiles_w, tiles_h, cblocks, items;
+};
+
+template <int K, int CG, int TWS, int TH>
+struct DwsBCfg {
+    using F = DwsCfg<K, CG, TWS, TH>;
+    static constexpr int KK = K * K;
+    static constexpr int GB_BYTES = F::XB_BYTES, XW_BYTES = F::XW_BYTES;
+    static constexpr int WS_BYTES = (CG * KK * 2 + 15) / 16 * 16, DW_BYTES = CG * KK * 4, CO_BYTES = 7 * CG * 4;
+    static constexpr int SMEM = 2 * GB_BYTES + XW_BYTES + WS_BYTES + DW_BYTES + CO_BYTES + 2 * CG * 4 + 16;
+    static constexpr int BY_REGS = 65536 / (F::THREADS * 128) < 1 ? 1 : 65536 / (F::THREADS * 128);
+    static constexpr int BY_SMEM = 232448 / (SMEM + 1024);
+    static constexpr int MINB = BY_REGS < BY_SMEM ? BY_REGS : (BY_SMEM < 1 ? 1 : BY_SMEM);
+};
+
+// dX row O of the tile: stage for the TMA store; reduce dX' = dX * [s_in x + t_in > 0] and dX' * x against the raw X
+template <int K, int CG, int TWS>
+struct DwsEmitReduce {
+    uint32_t out_lane, x_lane;
+    bool do_red;
+    f2_t sp, tp, mk0, mk1;
+    f2_t rs[2];
+    template <int O>
+    __device__ __forceinline__ void emit(float (&a)[4], bool row_ok) {
+        using F = DwmCfg<K, CG, TWS>;
+        const uint32_t u0 = pack_bf16x2(a[0], a[1]), u1 = pack_bf16x2(a[2], a[3]);
+        sts32(out_lane + O * F::OROWB, u0);
+        sts32(out_lane + O * F::OROWB + 8 * F::PITCH, u1);
+        if (do_red) {
+            const f2_t zero = f2_pack(0.f, 0.f), one = f2_pack(1.f, 1.f);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const f2_t x = f2_from_bf16x2(lds32(x_lane + O * F::OROWB + h * 8 * F::PITCH));
+                float y0, y1, q0, q1;
+                f2_unpack(f2_fma(sp, x, tp), y0, y1);
+                f2_unpack(f2_from_bf16x2(h ? u1 : u0), q0, q1);
+                f2_t q = f2_pack(y0 > 0.f ? q0 : 0.f, y1 > 0.f ? q1 : 0.f);
+                q = f2_fma(q, row_ok ? (h ? mk1 : mk0) : zero, zero);
+                rs[0] = f2_fma(q, one, rs[0]);
+                rs[1] = f2_fma(q, x, rs[1]);
+            }
+        }
+    }
+};
+
+template <int K, int CG, int TWS, int TH>
+__global__ void __launch_bounds__(DwsCfg<K, CG, TWS, TH>::THREADS, DwsBCfg<K, CG, TWS, TH>::MINB)
+    dws_bwd_k(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_x,
+              const __grid_constant__ CUtensorMap tm_dx, const DwsBP p) {
+    using Cfg = DwsCfg<K, CG, TWS, TH>;
+    using B = DwsBCfg<K, CG, TWS, TH>;
+    constexpr int P = Cfg::P, NCH = Cfg::NCH, TW = Cfg::TW, HC = Cfg::HC, PITCH = Cfg::PITCH, THREADS = Cfg::THREADS, TR = Cfg::TR;
+    constexpr int KK = K * K, NPR = (K + 1) / 2;
+    extern __shared__ __align__(128) unsigned char dsm[];
+    const uint32_t GB = smem_u32(dsm);                      // G tile -> dZ (in place)
+    const uint32_t ZB = GB + B::GB_BYTES;                   // Z tile; after the transform: dX staging (TH x TW)
+    const uint32_t XW = ZB + B::GB_BYTES;                   // raw X tile
+    unsigned char* after = dsm + 2 * B::GB_BYTES + B::XW_BYTES;
+    __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(after);                           // [CG][KK] bf16
+    float* dwacc = reinterpret_cast<float*>(after + B::WS_BYTES);                           // [CG][KK]
+    float* coef = reinterpret_cast<float*>(after + B::WS_BYTES + B::DW_BYTES);              // [7][CG]
+    float* red = coef + 7 * CG;                                                             // [2][CG]
+    const uint32_t bar = smem_u32(red + 2 * CG);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int chunk = warp % NCH, strip = warp / NCH;
+    const int cb = blockIdx.x % p.cblocks, slot = blockIdx.x / p.cblocks, nslots = gridDim.x / p.cblocks;
+    const int cbase = cb * CG;
+    const bool chunk_live = cbase + chunk * 8 < p.C;
+    const bool do_wgrad = p.dw != nullptr, do_red = p.nsums != nullptr && p.in_scale != nullptr;
+
+    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < CG * KK; i += THREADS) {
+        const int c = cbase + i / KK;
+        wsm[i] = __float2bfloat16_rn(c < p.C ? p.w[(size_t)c * KK + i % KK] : 0.f);
+        dwacc[i] = 0.f;
+    }
+    for (int i = tid; i < CG; i += THREADS) {
+        // the per-channel work of BatchNorm backward (what bn_bwd_finalize does), redundantly per CTA
+        const int c = cbase + i;
+        float a = 0.f, b = 0.f, c3 = 0.f, sc = 0.f, sh = 0.f, isc = 1.f, ish = 0.f;
+        if (c < p.C) {
+            const double sg = p.sums[c], sgz = p.sums[p.C + c];
+            const double mean = p.mean[c], invstd = p.invstd[c], s = p.scale[c];
+            const double dga = invstd * (sgz - mean * sg);
+            const double bb = -s * invstd * dga / p.m;
+            const double cc = -s * sg / p.m - bb * mean;
+            a = (float)s; b = (float)bb; c3 = (float)cc; sc = p.scale[c]; sh = p.shift[c];
+            if (p.in_scale) { isc = p.in_scale[c]; ish = p.in_shift[c]; }
+            if (slot == 0) {
+                if (p.dgamma) p.dgamma[c] += (float)dga;
+                if (p.dbeta) p.dbeta[c] += (float)sg;
+                if (p.dbias) p.dbias[c] += (float)(s * sg + bb * mean * p.m + cc * p.m);   // analytically 0
+            }
+        }
+        coef[0 * CG + i] = a; coef[1 * CG + i] = b; coef[2 * CG + i] = c3; coef[3 * CG + i] = sc; coef[4 * CG + i] = sh;
+        coef[5 * CG + i] = isc; coef[6 * CG + i] = ish;
+        red[i] = 0.f; red[CG + i] = 0.f;
+    }
+    const int tchunk = tid % NCH, pix0 = tid / NCH;
+    constexpr int PSTEP = THREADS / NCH;
+    const bool tlive = cbase + tchunk * 8 < p.C;
+    const int mi = lane >> 3, r8 = lane & 7;
+    const uint32_t off4 = (uint32_t)(((mi >> 1) + (mi & 1) * 8 + r8 + strip * 16) * PITCH + chunk * 16);
+    const uint32_t off2 = (uint32_t)(((K - 1) + (mi & 1) * 8 + r8 + strip * 16) * PITCH + chunk * 16);
+    const uint32_t offx = (uint32_t)(((mi & 1) * 8 + r8 + strip * 16) * PITCH + chunk * 16);
+    typedef DwsEmitReduce<K, CG, TWS> EM;
+    EM em;
+    em.out_lane = ZB + (uint32_t)((strip * 16 + g) * PITCH + chunk * 16 + t * 4);
+    em.x_lane = XW + (uint32_t)(P * Cfg::OROWB + (strip * 16 + g) * PITCH + chunk * 16 + t * 4);
+    em.do_red = do_red;
+    em.rs[0] = em.rs[1] = f2_pack(0.f, 0.f);
+    uint32_t ph = 0;
+    __syncthreads();
+    {
+        const int c = chunk * 8 + 2 * t;
+        em.sp = f2_pack(coef[5 * CG + c], coef[5 * CG + c + 1]);
+        em.tp = f2_pack(coef[6 * CG + c], coef[6 * CG + c + 1]);
+    }
+    const f2_t ag = f2_pack(coef[5 * CG + chunk * 8 + g], coef[5 * CG + chunk * 8 + g]);
+    const f2_t at = f2_pack(coef[6 * CG + chunk * 8 + g], coef[6 * CG + chunk * 8 + g]);
+    const bool act = p.in_scale != nullptr;
+    const int per_img = p.tiles_w * p.tiles_h;
+
+    for (int item = slot; item < p.items; item += nslots) {
+        const int n = item / per_img, rem = item - n * per_img, wt = rem / p.tiles_h, rt = rem - wt * p.tiles_h;
+        const int w0 = wt * TW, o0 = rt * TH, r0 = o0 - P;
+        if (tid == 0) {
+            tma_store_wait_read();                      // the previous tile's dX store has finished reading ZB
+            mbar_expect_tx(bar, (uint32_t)(2 * TR * Cfg::ROWB + TR * Cfg::OROWB));
+            tma_load4(GB, &tm_g, cbase, w0 - P, r0, n, bar);
+            tma_load4(ZB, &tm_z, cbase, w0 - P, r0, n, bar);
+            tma_load4(XW, &tm_x, cbase, w0, r0, n, bar);
+        }
+        mbar_wait(bar, ph);
+        ph ^= 1;
+        if (tlive) {
+            // dZ = a * G * [scale*Z + shift > 0] + b * Z + c in place over G (zero outside the image)
+            f2_t ca[4], cb2[4], cc[4], cs[4], ct[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = tchunk * 8 + 2 * i;
+                ca[i] = f2_pack(coef[c], coef[c + 1]);
+                cb2[i] = f2_pack(coef[CG + c], coef[CG + c + 1]);
+                cc[i] = f2_pack(coef[2 * CG + c], coef[2 * CG + c + 1]);
+                cs[i] = f2_pack(coef[3 * CG + c], coef[3 * CG + c + 1]);
+                ct[i] = f2_pack(coef[4 * CG + c], coef[4 * CG + c + 1]);
+            }
+            for (int pix = pix0; pix < TR * HC; pix += PSTEP) {
+                const int rr = pix / HC, cc_ = pix - rr * HC;
+                if ((unsigned)(r0 + rr) < (unsigned)p.H && (unsigned)(w0 - P + cc_) < (unsigned)p.W) {
+                    const uint32_t o = (uint32_t)(pix * PITCH + tchunk * 16);
+                    const uint4 ug = lds128(GB + o), uz = lds128(ZB + o);
+                    const uint32_t gg[4] = {ug.x, ug.y, ug.z, ug.w}, zz[4] = {uz.x, uz.y, uz.z, uz.w};
+                    uint32_t r[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const f2_t z2 = f2_from_bf16x2(zz[i]);
+                        float y0, y1, g0, g1, d0, d1;
+                        f2_unpack(f2_fma(cs[i], z2, ct[i]), y0, y1);
+                        f2_unpack(f2_from_bf16x2(gg[i]), g0, g1);
+                        const f2_t gm = f2_pack(y0 > 0.f ? g0 : 0.f, y1 > 0.f ? g1 : 0.f);
+                        f2_unpack(f2_fma(ca[i], gm, f2_fma(cb2[i], z2, cc[i])), d0, d1);
+                        r[i] = pack_bf16x2(d0, d1);
+                    }
+                    sts128(GB + o, make_uint4(r[0], r[1], r[2], r[3]));
+                }
+            }
+        }
+        __syncthreads();
+        const int sw = w0 + strip * 16;
+        if (chunk_live && sw < p.W) {
+            const float m0 = sw + g < p.W ? 1.f : 0.f, m1 = sw + g + 8 < p.W ? 1.f : 0.f;
+            em.mk0 = f2_pack(m0, m0);
+            em.mk1 = f2_pack(m1, m1);
+            {   // (a) backward-data: rotated diagonal weight fragments, rebuilt per tile (dead during (b))
+                uint32_t bd[K][K];
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw) {
+                        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(wsm[(chunk * 8 + g) * KK + (K - 1 - kh) * K + (K - 1 - kw)]);
+                        bd[kh][kw] = (g >> 1) == t ? ((g & 1) ? (hb << 16) : hb) : 0u;
+                    }
+                float acc[K][4];
+#pragma unroll
+                for (int i = 0; i < K; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                DwsRows<K, CG, TWS, TH, 0, EM>::run(acc, bd, GB + off4, GB + off2, o0, p.H, em, 0u, 0u);
+            }
+            if (do_wgrad) {
+                // (b) backward-weight: dZ tile row P + o (image row o0 + o) pairs with X tile rows o .. o + K - 1
+                const uint32_t gz4 = GB + P * Cfg::ROWB + off4, gz2 = GB + P * Cfg::ROWB + off2, xrow = XW + offx;
+                const int c0 = sw + 2 * t;
+                const uint32_t cm0 = (c0 < p.W ? 0x0000ffffu : 0u) | (c0 + 1 < p.W ? 0xffff0000u : 0u);
+                const uint32_t cm1 = (c0 + 8 < p.W ? 0x0000ffffu : 0u) | (c0 + 9 < p.W ? 0xffff0000u : 0u);
+                auto load_x = [&](int xr, uint32_t (&dst)[2]) {
+                    const bool rv = (unsigned)(r0 + xr) < (unsigned)p.H;
+                    uint32_t u0, u1;
+                    ldsm2t(xrow + (uint32_t)(xr * Cfg::OROWB), u0, u1);
+                    if (act) {
+                        u0 = f2_relu_bf16x2(f2_fma(f2_from_bf16x2(u0), ag, at));
+                        u1 = f2_relu_bf16x2(f2_fma(f2_from_bf16x2(u1), ag, at));
+                    }
+                    dst[0] = rv ? u0 & cm0 : 0u;
+                    dst[1] = rv ? u1 & cm1 : 0u;
+                };
+                float wacc[K][NPR][4];
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+                    for (int pr = 0; pr < NPR; ++pr) wacc[kh][pr][0] = wacc[kh][pr][1] = wacc[kh][pr][2] = wacc[kh][pr][3] = 0.f;
+                uint32_t bf[K][2];
+#pragma unroll
+                for (int kh = 0; kh + 1 < K; ++kh) load_x(kh, bf[kh]);
+#pragma unroll
+                for (int o = 0; o < TH; ++o) {
+                    load_x(o + K - 1, bf[(o + K - 1) % K]);
+                    uint32_t tt[K][2];
+                    const uint32_t a4 = gz4 + (uint32_t)(o * Cfg::ROWB), a2 = gz2 + (uint32_t)(o * Cfg::ROWB);
+                    ldsm4t(a4, tt[0][0], tt[0][1], tt[1][0], tt[1][1]);
+                    if constexpr (K == 5) ldsm4t(a4 + 2 * PITCH, tt[2][0], tt[2][1], tt[3][0], tt[3][1]);
+                    ldsm2t(a2, tt[K - 1][0], tt[K - 1][1]);
+#pragma unroll
+                    for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+                        for (int pr = 0; pr < NPR; ++pr) {
+                            const int s0 = 2 * pr, s1 = (2 * pr + 1 < K) ? 2 * pr + 1 : 2 * pr;
+                            mma16816(wacc[kh][pr], tt[s0][0], tt[s1][0], tt[s0][1], tt[s1][1], bf[(o + kh) % K][0], bf[(o + kh) % K][1]);
+                        }
+                }
+                if ((g >> 1) == t) {
+                    float* dst = dwacc + (chunk * 8 + g) * KK;
+#pragma unroll
+                    for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+                        for (int pr = 0; pr < NPR; ++pr) {
+                            atomicAdd(dst + kh * K + (K - 1 - 2 * pr), (g & 1) ? wacc[kh][pr][1] : wacc[kh][pr][0]);
+                            if (2 * pr + 1 < K) atomicAdd(dst + kh * K + (K - 2 - 2 * pr), (g & 1) ? wacc[kh][pr][3] : wacc[kh][pr][2]);
+                        }
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) tma_store4(&tm_dx, cbase, w0, o0, n, ZB);
+    }
+    if (tid == 0) tma_store_wait_read();
+    if (do_red) {
+        float v[4];
+        f2_unpack(em.rs[0], v[0], v[1]);
+        f2_unpack(em.rs[1], v[2], v[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 4);
+            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
+            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+        }
+        if (g == 0 && chunk_live) {
+            const int c = chunk * 8 + 2 * t;
+            atomicAdd(&red[c], v[0]);
+            atomicAdd(&red[c + 1], v[1]);
+            atomicAdd(&red[CG + c], v[2]);
+            atomicAdd(&red[CG + c + 1], v[3]);
+        }
+    }
+    __syncthreads();
+    if (do_red) {
+        for (int i = tid; i < CG; i += THREADS)
+            if (cbase + i < p.C) {
+                atomicAdd(&p.nsums[cbase + i], (double)red[i]);
+                atomicAdd(&p.nsums[p.C + cbase + i], (double)red[CG + i]);
+            }
+    }
+    if (do_wgrad) {
+        for (int i = tid; i < CG * KK; i += THREADS)
+            if (cbase + i / KK < p.C) atomicAdd(&p.dw[(size_t)cbase * KK + i], dwacc[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 static bool dws_fill(DwsP& p, const DwmGeom& g, int N, int H, int W, int C, int TH) {
@@ -463,6 +764,58 @@ int dw_wgrad_small(const void* x, const float* s, const float* t, const void* dz
                    cudaStream_t st) {
     if (k == 3) return dws_wgrad_any<3>(x, s, t, dz, dw, N, H, W, C, st, "dw_wgrad(small)");
     return dws_wgrad_any<5>(x, s, t, dz, dw, N, H, W, C, st, "dw_wgrad(small)");
+}
+
+template <int K, int CG, int TWS, int TH>
+static int dws_launch_bwd(const DwmGeom& g, DwsBP p, const void* G, const void* Z, const void* X, void* dX, cudaStream_t st,
+                          const char* name) {
+    using Cfg = DwsCfg<K, CG, TWS, TH>;
+    using B = DwsBCfg<K, CG, TWS, TH>;
+    const int N = p.N, H = p.H, W = p.W, C = p.C;
+    CUtensorMap tm_g, tm_z, tm_x, tm_dx;
+    if (int e = dwm_tensor_map(&tm_g, G, N, H, W, C, CG, Cfg::HC, Cfg::TR)) return e;
+    if (int e = dwm_tensor_map(&tm_z, Z, N, H, W, C, CG, Cfg::HC, Cfg::TR)) return e;
+    if (int e = dwm_tensor_map(&tm_x, X, N, H, W, C, CG, Cfg::TW, Cfg::TR)) return e;
+    if (int e = dwm_tensor_map(&tm_dx, dX, N, H, W, C, CG, Cfg::TW, TH)) return e;
+    p.tiles_w = g.tiles_w; p.tiles_h = (H + TH - 1) / TH; p.cblocks = g.cblocks;
+    const long long items = (long long)N * p.tiles_w * p.tiles_h;
+    if (items > (1 << 24)) return MNB_ERR_UNSUPPORTED;
+    p.items = (int)items;
+    static int occ = -1;
+    if (occ < 0) {
+        cudaError_t e = cudaFuncSetAttribute(dws_bwd_k<K, CG, TWS, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM);
+        if (e != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dws_bwd_k<K, CG, TWS, TH>, Cfg::THREADS, B::SMEM);
+        if (o < 1) { set_error("%s: kernel does not fit on an SM", name); return MNB_ERR_UNSUPPORTED; }
+        occ = o;
+    }
+    long long slots = (long long)num_sms() * occ / p.cblocks;
+    if (slots < 1) slots = 1;
+    if (slots > p.items) slots = p.items;
+    dws_bwd_k<K, CG, TWS, TH><<<(unsigned)(slots * p.cblocks), Cfg::THREADS, B::SMEM, st>>>(tm_g, tm_z, tm_x, tm_dx, p);
+    MNB_LAUNCH_CHECK(name);
+    return 0;
+}
+
+int dw_bwd_small(const void* G, const void* Z, const float* scale, const float* shift, const double* sums, const float* mean,
+                 const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
+                 const float* in_scale, const float* in_shift, const float* w, void* dX, float* dw, double* nsums, int N, int H,
+                 int W, int C, int k, cudaStream_t st) {
+    DwsBP p = {};
+    p.scale = scale; p.shift = shift; p.sums = sums; p.mean = mean; p.invstd = invstd; p.m = m;
+    p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias; p.in_scale = in_scale; p.in_shift = in_shift; p.w = w; p.dw = dw;
+    p.nsums = nsums; p.N = N; p.H = H; p.W = W; p.C = C;
+    const DwmGeom g = dwm_geometry(C, W, k);
+    const char* name = "dw_bwd(small)";
+    const bool th7 = H <= 7;
+#define CALL3(CGG, TT) return th7 ? dws_launch_bwd<3, CGG, TT, 7>(g, p, G, Z, X, dX, st, name) : dws_launch_bwd<3, CGG, TT, 14>(g, p, G, Z, X, dX, st, name);
+#define CALL5(CGG, TT) return th7 ? dws_launch_bwd<5, CGG, TT, 7>(g, p, G, Z, X, dX, st, name) : dws_launch_bwd<5, CGG, TT, 14>(g, p, G, Z, X, dX, st, name);
+    if (k == 3) { DWS_DISPATCH(CALL3) }
+    if (k == 5) { DWS_DISPATCH(CALL5) }
+#undef CALL3
+#undef CALL5
+    return MNB_ERR_UNSUPPORTED;
 }
 
 }  // namespace mnb

@@ -308,6 +308,10 @@ int dw_fwd_small(const void* x, const float* s, const float* t, const float* w, 
 int dw_dgrad_small(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
 int dw_wgrad_small(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W, int C, int k,
                    cudaStream_t st);
+int dw_bwd_small(const void* G, const void* Z, const float* scale, const float* shift, const double* sums, const float* mean,
+                 const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
+                 const float* in_scale, const float* in_shift, const float* w, void* dX, float* dw, double* nsums, int N, int H,
+                 int W, int C, int k, cudaStream_t st);
 int pw_bwd_fused(const void* G, const void* Z, const float* scale, const float* shift, const double* sums, const float* mean,
                  const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
                  const float* in_scale, const float* in_shift, const float* w, const void* add, void* dX, float* dw,
@@ -431,6 +435,11 @@ int mnb_dw_bwd_fused(const void* dA, const void* z, const float* scale, const fl
     MNB_REQUIRE(!in_scale || in_shift, "dw_bwd_fused: in_scale without in_shift");
     MNB_REQUIRE(m > 0, "dw_bwd_fused: bad element count");
     if (dtype != MNB_BF16) { set_error("dw_bwd_fused: bf16 only"); return MNB_ERR_UNSUPPORTED; }
+    if (dw_small_covers(H, W, C, k)) {
+        int r = dw_bwd_small(dA, z, scale, shift, sums, save_mean, save_invstd, m, dgamma, dbeta, dbias, x, in_scale, in_shift,
+                             w, dx, dw, in_sums, N, H, W, C, k, (cudaStream_t)stream);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     return dw_bwd_mma(dA, z, scale, shift, sums, save_mean, save_invstd, m, dgamma, dbeta, dbias, x, in_scale, in_shift, w,
                       dx, dw, in_sums, N, H, W, C, k, (cudaStream_t)stream);
 }

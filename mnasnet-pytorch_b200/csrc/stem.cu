@@ -302,6 +302,9 @@ __global__ void __launch_bounds__(128, 4) stem_wgrad_mma_k(const void* __restric
     }
 }
 
+int stem_fwd_mma(const void* x, int x_u8, const float* mean, const float* stdv, const float* w, const float* bias, void* z,
+                 double* stats, int N, int H, int W, cudaStream_t st);
+
 bool stem_supported(int Cin, int Cout, int k, int stride, int pad, int nchw_in) {
     return nchw_in && Cin == 3 && Cout == 32 && k == 3 && stride == 2 && pad == 1;
 }
@@ -314,6 +317,11 @@ int stem_fwd(const void* x, int x_u8, const float* mean, const float* stdv, cons
     long long blocks = cdiv(total, 128);
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
+    // bf16: tensor-pipe kernel (stem_mma.cu) unless the "stem_mma" option / MNB_STEM_MMA is 0 or the rows cannot be bulk-copied
+    if (dtype == MNB_BF16 && option_get(OPT_STEM_MMA)) {
+        int r = stem_fwd_mma(x, x_u8, mean, stdv, w, bias, z, stats, N, H, W, st);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
+    }
     const unsigned b = (unsigned)blocks;
     if (dtype == MNB_F32) {
         if (x_u8) stem_fwd_k<float, 32, true><<<b, 128, 0, st>>>(x, mean, stdv, w, bias, (float*)z, stats, N, H, W, Ho, Wo);

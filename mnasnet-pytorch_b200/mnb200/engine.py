@@ -14,6 +14,7 @@ backward-ready-first so NCCL buckets are contiguous slices; nn.Parameters are vi
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import List, Optional
 
@@ -642,9 +643,11 @@ class Plan:
             ops.append(_EventOp("wait", self.side_last, 0))      # join: optimizer / caller see all weight grads
 
     def _fused_dw_backward(self, a, idx, first_live) -> bool:
-        """Where the fused depthwise backward kernel is used: bf16, 3x3 on maps of >= 56 rows with a channel count the
-        24-channel geometry tiles exactly -- the layers where it measured faster than the unfused chain
-        (profiles/r2_exp_dw_mma.json); the input must come straight from a ConvBlock (raw z + scale / shift)."""
+        """Where the fused depthwise backward kernels are used (bf16; the input must come straight from a ConvBlock: raw z
+        + scale / shift) -- the layers where they measured faster than the unfused chain: the row-streaming kernel
+        (dw_mma.cu) for 3x3 on maps of >= 56 rows with a channel count the 24-channel geometry tiles exactly
+        (profiles/r2_exp_dw_mma.json), the whole-tile kernel (dw_small.cu) on the 28 x 28 and 14 x 14 maps
+        (scripts/exp_dw_small.py bwd: 242 vs 277, 148 vs 172, 76 vs 136 us)."""
         eng = self.eng
         if eng.dtype != "bf16" or not eng.fuse_dw_bwd or a.kind != "dw":
             return False
@@ -655,6 +658,8 @@ class Plan:
             return False
         if eng.fuse_dw_bwd == 2:                 # forced (tests): every shape the kernel supports
             return r.H >= 1
+        if 12 <= r.H <= 28 and r.W >= 12 and _lib.get_option("dw_small") == 1:
+            return True
         return a.k == 3 and r.H >= 56 and r.W >= 24 and a.Cout % 24 == 0
 
     PW_FUSED_SHAPES = {(16, 48), (48, 16), (32, 16), (24, 72), (72, 24)}       # (Cin, Cout) instantiated in pw_bwd_fused.cu
@@ -876,7 +881,8 @@ class Engine:
         self.side_stream = torch.cuda.Stream(device=self.device)
         self.fuse_bn_reduce = False    # BN-backward reductions in the producing dgrad epilogue (tested; off:
                                        # the dgrad epilogues are the bottleneck, the separate kernel is faster)
-        self.fuse_dw_bwd = 1           # fused depthwise ConvBlock backward (csrc/dw_mma.cu): 0 off, 1 where it wins, 2 always
+        # fused depthwise ConvBlock backward (csrc/dw_mma.cu): 0 off, 1 where it wins, 2 always (MNB_FUSE_DW_BWD overrides)
+        self.fuse_dw_bwd = int(os.environ.get("MNB_FUSE_DW_BWD", "1"))
         self.fuse_pw_bwd = 1           # fused pointwise ConvBlock backward (csrc/pw_bwd_fused.cu) for its shapes
         self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
         self.optimizer = "adam"        # 'adam' | 'rmsprop' | 'sgd' (train.py:218-231); set before the first graph capture

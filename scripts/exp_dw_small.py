@@ -103,3 +103,40 @@ if __name__ == "__main__":
             timing(H, C, k)
         for (H, C, k) in [(7, 1152, 5), (7, 1152, 3)]:
             timing(H, C, k, on=2)
+
+
+def bwd_timing(H, C, k, N=256):
+    """fused mnb_dw_bwd_fused (dw_small) vs the unfused chain bn_bwd_apply_fused + dw_dgrad + dw_wgrad + bn_bwd_reduce(producer)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M = N * H * H
+    x = torch.randn(N, H, H, C, device="cuda", generator=g).to(BF)
+    z = (torch.randn(N, H, H, C, device="cuda", generator=g) * 0.7 + 0.2).to(BF)
+    dA = torch.randn(N, H, H, C, device="cuda", generator=g).to(BF)
+    w = (torch.randn(C, 1, k, k, device="cuda", generator=g) / k).float()
+    sc, isc = ((torch.rand(C, device="cuda", generator=g) + 0.5).float() for _ in range(2))
+    sh, ish = ((torch.randn(C, device="cuda", generator=g) * 0.3).float() for _ in range(2))
+    mean = z.float().mean(dim=(0, 1, 2)).contiguous(); inv = (1 / torch.sqrt(z.float().var(dim=(0, 1, 2), unbiased=False) + 1e-5)).contiguous()
+    sums = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    L.call("mnb_bn_bwd_reduce", P(dA), P(z), P(sc), P(sh), P(sums), M, C, 1, S())
+    dz = torch.empty_like(z); dx = torch.empty_like(x); dw = torch.zeros_like(w)
+    ns = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    dga, dbe, dbi = (torch.zeros(C, device="cuda") for _ in range(3))
+    def unfused():
+        L.call("mnb_bn_bwd_apply_fused", P(dA), P(z), P(sc), P(sh), P(sums), P(mean), P(inv), P(dga), P(dbe), P(dbi), P(dz), M, C, float(M), 1, S())
+        L.call("mnb_dw_dgrad", P(dz), P(w), P(dx), None, None, None, None, N, H, H, C, k, 1, S())
+        L.call("mnb_dw_wgrad", P(x), P(isc), P(ish), P(dz), P(dw), N, H, H, C, k, 1, S())
+        L.call("mnb_bn_bwd_reduce", P(dx), P(x), P(isc), P(ish), P(ns), M, C, 1, S())
+    def fused():
+        L.call("mnb_dw_bwd_fused", P(dA), P(z), P(sc), P(sh), P(sums), P(mean), P(inv), P(dga), P(dbe), P(dbi), P(x), P(isc), P(ish),
+               P(w), P(dx), P(dw), P(ns), N, H, H, C, k, float(M), 1, S())
+    row = {"shape": f"{N}x{H}x{H}x{C} k{k}", "unfused_us": round(timeit(unfused), 1), "fused_small_us": round(timeit(fused), 1)}
+    L.set_option("dw_small", 0)
+    row["fused_stream_us"] = round(timeit(fused), 1)
+    L.set_option("dw_small", 1)
+    row["fused_frac_hbm"] = round(4 * M * C * 2 / row["fused_small_us"] / 1e3 / 6546.6 * 1e3 / 1e3, 3)
+    print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__" and "bwd" in sys.argv[1:]:
+    for (H, C, k) in [(28, 240, 5), (14, 576, 5), (14, 480, 3), (28, 72, 5)]:
+        bwd_timing(H, C, k)

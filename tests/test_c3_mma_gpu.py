@@ -93,3 +93,46 @@ def test_c3_mma_agrees_with_the_tcgen05_path():
         res.append((z.float(), st, dx.float(), dw))
     for a, b in zip(*res):
         assert rel(a, b) < 5e-3
+
+
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("N,H,W", [(2, 224, 224), (2, 64, 96), (1, 32, 48), (3, 30, 28), (2, 17, 16), (1, 448, 448)])
+def test_stem_forward_on_the_tensor_pipe(N, H, W, u8):
+    """features.0 forward in bf16 mode (csrc/stem_mma.cu: bulk-copied rows, im2col tile, mma.sync) for fp32 NCHW and uint8
+    NHWC input against torch fp32 math on the bf16-rounded operands; shapes whose rows cannot be bulk-copied (W*3 % 16)
+    or that are too wide (448) fall back to the CUDA-core kernel, which must agree to bf16 rounding (src/models/mnasnet.py:179)."""
+    from mnb200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(H + W)
+    w = (torch.randn(32, 3, 3, 3, device="cuda", generator=g) / 5).float()
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda")
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda")
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if u8:
+        x8 = torch.randint(0, 256, (N, H, W, 3), device="cuda", generator=g, dtype=torch.uint8)
+        xn = ((x8.permute(0, 3, 1, 2).float() / 255) - mean[None, :, None, None]) / std[None, :, None, None]
+        args = (P(x8), P(mean), P(std))
+        layout = L.LAYOUT_NHWC_U8
+    else:
+        xn = torch.randn(N, 3, H, W, device="cuda", generator=g)
+        args = (P(xn), None, None)
+        layout = L.LAYOUT_NCHW_F32
+    res = []
+    old = L.get_option("stem_mma")
+    try:
+        for opt in (1, 0):
+            L.set_option("stem_mma", opt)
+            z = torch.full((N, Ho, Wo, 32), float("nan"), device="cuda", dtype=BF)
+            st = torch.zeros(64, device="cuda", dtype=torch.float64)
+            L.call("mnb_conv_fwd", args[0], args[1], args[2], P(w), None, P(z), P(st), N, H, W, 3, 32, 3, 2, 1, 1, layout, 0, S())
+            torch.cuda.synchronize()
+            res.append((z, st))
+    finally:
+        L.set_option("stem_mma", old)
+    z, st = res[0]
+    zr = F.conv2d(xn.to(BF).float(), w.to(BF).float(), None, stride=2, padding=1)
+    assert not torch.isnan(z.float()).any()
+    assert rel(z.float().permute(0, 3, 1, 2), zr) < 5e-3
+    zs = z.double()
+    torch.testing.assert_close(st[:32], zs.sum(dim=(0, 1, 2)), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(st[32:], (zs * zs).sum(dim=(0, 1, 2)), rtol=1e-5, atol=1e-4)
+    assert rel(z.float(), res[1][0].float()) < 1e-2            # the CUDA-core kernel keeps fp32 operands

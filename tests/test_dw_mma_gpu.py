@@ -90,10 +90,21 @@ def test_dw_mma_forward_dgrad_wgrad(case, xform, forced_mma):
 
 @pytest.mark.parametrize("act", [True, False])
 @pytest.mark.parametrize("case", CASES)
-def test_dw_fused_backward_matches_torch(case, act):
+@pytest.mark.parametrize("small", [0, 2])
+def test_dw_fused_backward_matches_torch(case, act, small):
     """mnb_dw_bwd_fused vs the SURVEY appendix-F math in fp64: G = dA*[scale*z+shift>0]; dZ = a*G + b*z + c;
-    dx = conv_dgrad(dZ); dw += conv_wgrad(A, dZ); dgamma/dbeta; reductions of dx for the producing block."""
+    dx = conv_dgrad(dZ); dw += conv_wgrad(A, dZ); dgamma/dbeta; reductions of dx for the producing block.
+    small = 0: the row-streaming kernel (dw_mma.cu) on every map; 2: the whole-tile kernel (dw_small.cu) on maps <= 28 rows."""
     from mnb200 import _lib as L
+    old_small = L.get_option("dw_small")
+    L.set_option("dw_small", small)
+    try:
+        _fused_backward_case(L, case, act)
+    finally:
+        L.set_option("dw_small", old_small)
+
+
+def _fused_backward_case(L, case, act):
     N, H, W, C, k = case
     g = torch.Generator(device="cuda").manual_seed(5 + 31 * H + C)
     x = torch.randn(N, H, W, C, device="cuda", generator=g).to(BF)

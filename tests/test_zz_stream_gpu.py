@@ -321,8 +321,26 @@ def test_uint8_input_fused_into_the_stem(dtype):
     for k, p in m.named_parameters():          # (the stem gradient sits behind every ReLU mask of the network: F9 noise)
         if k.startswith("classifier"):
             assert rel(p.grad, g_ref[k]) < (1e-3 if dtype == "fp32" else 0.3), k
-        elif k == "features.0.conv.weight":
-            assert rel(p.grad, g_ref[k]) < (8e-2 if dtype == "fp32" else 0.6), k
+        elif k == "features.0.conv.weight" and dtype == "fp32":
+            assert rel(p.grad, g_ref[k]) < 8e-2, k
+    # bf16: a 3-image batch leaves 18 elements per channel in the last stage's BatchNorm, so the stem gradient of two runs
+    # is uncorrelated noise (rel-L2 0.6-0.75 measured between IDENTICAL runs); the stem backward-weight is compared
+    # teacher-forced instead: same dZ through the uint8 kernel and through the normalise-first fp32 NCHW kernel
+    from mnb200 import _lib as ML
+    code = ML.MNB_F32 if dtype == "fp32" else ML.MNB_BF16
+    zt = plan.apps[0].z
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    dz = torch.randn(zt.shape, device="cuda", generator=gen).to(zt.dtype)
+    mean_t, std_t = eng.norm_constants()
+    w0 = m.features[0].conv.weight
+    dw_u8, dw_f = torch.zeros_like(w0), torch.zeros_like(w0)
+    x8d = x8.cuda().contiguous()
+    ML.call("mnb_conv_wgrad", x8d.data_ptr(), mean_t.data_ptr(), std_t.data_ptr(), dz.data_ptr(), dw_u8.data_ptr(), 3, 64, 96, 3,
+            32, 3, 2, 1, code, ML.LAYOUT_NHWC_U8, eng.impl, torch.cuda.current_stream().cuda_stream)
+    ML.call("mnb_conv_wgrad", y.data_ptr(), None, None, dz.data_ptr(), dw_f.data_ptr(), 3, 64, 96, 3, 32, 3, 2, 1, code,
+            ML.LAYOUT_NCHW_F32, eng.impl, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel(dw_u8, dw_f) < 1e-5
     # and against the CPU oracle on the torch-normalised input (fp32): the whole uint8 path is the reference's
     if dtype == "fp32":
         mean = torch.tensor(m.mean)[None, :, None, None]
