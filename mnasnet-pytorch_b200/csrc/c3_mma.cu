@@ -481,10 +481,12 @@ __global__ void __launch_bounds__(C3WCfg<CIN, COUT>::THREADS, C3WCfg<CIN, COUT>:
         ph ^= 1u << b;
         if (xf) c3_transform<CIN, THREADS>(XB, s_sc, iy0, p.BH, p.H, p.RP, tid);
         __syncthreads();
+        // this lane's pixel of the k-step (B operand row): walks 16 pixels per step through the TH x TWO tile
+        int pb0 = (mi & 1) * 8 + r8;
+        int ty = (int)fastdiv((uint32_t)pb0, p.magic_two), tx = pb0 - ty * p.TWO;
+        const int dty = (int)fastdiv(16u, p.magic_two), dtx = 16 - dty * p.TWO;
         for (int ks = 0; ks < nk; ++ks) {
-            int pb = ks * 16 + (mi & 1) * 8 + r8;
-            pb = pb < p.PT ? pb : p.PT - 1;
-            const int ty = (int)fastdiv((uint32_t)pb, p.magic_two), tx = pb - ty * p.TWO;
+            if (ty >= p.TH) { ty = p.TH - 1; tx = p.TWO - 1; }        // beyond the tile: any valid pixel (its dz rows are zero)
             const int ix = tx * S - 1 + kx;
             const uint32_t baddr = ((unsigned)ix < (unsigned)p.W ? XB + (uint32_t)(((ty * S + ky) * p.W + ix) * PITCH) : ZB);
             uint32_t bf[NTI][2], a[MTW][4];
@@ -498,6 +500,8 @@ __global__ void __launch_bounds__(C3WCfg<CIN, COUT>::THREADS, C3WCfg<CIN, COUT>:
             for (int i = 0; i < MTW; ++i)
 #pragma unroll
                 for (int j = 0; j < NTI; ++j) mma16816(acc[i][j], a[i][0], a[i][1], a[i][2], a[i][3], bf[j][0], bf[j][1]);
+            ty += dty; tx += dtx;
+            if (tx >= p.TWO) { tx -= p.TWO; ++ty; }
         }
         fence_proxy_async();        // the in-place transform / zero fill precede the next bulk write to this buffer
         __syncthreads();            // buffer b is free for the load issued at the top of the next iteration
@@ -557,8 +561,11 @@ template <class K>
 static int c3_launch(K kern, const C3P& q, int threads, size_t smem, cudaStream_t st, const char* name) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
-    const int per_sm = smem + 1024 <= 113 * 1024 ? 2 : 1;
-    const int grid = std::min(q.items, num_sms() * per_sm);
+    // persistent grid of resident CTAs only (registers and shared memory decide how many share an SM)
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (per_sm < 1) { set_error("%s: kernel does not fit on an SM", name); return MNB_ERR_UNSUPPORTED; }
+    const int grid = std::min(q.items, num_sms() * std::min(per_sm, 4));
     kern<<<grid, threads, smem, st>>>(q);
     MNB_LAUNCH_CHECK(name);
     return 0;

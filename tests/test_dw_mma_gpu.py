@@ -31,15 +31,17 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-@pytest.fixture()
-def forced_mma():
+@pytest.fixture(params=[0, 2], ids=["strips-default", "strips-2"])
+def forced_mma(request):
     from mnb200 import _lib as L
-    old, old_small = L.get_option("dw_mma"), L.get_option("dw_small")
+    old, old_small, old_tws = L.get_option("dw_mma"), L.get_option("dw_small"), L.get_option("dw_mma_tws")
     L.set_option("dw_mma", 2)           # 2 = every bf16 shape, not only the ones where it is the fastest kernel
     L.set_option("dw_small", 0)         # the whole-tile kernels (dw_small.cu, tests/test_dw_small_gpu.py) take the small maps otherwise
+    L.set_option("dw_mma_tws", request.param)   # 0 = default geometry (one 16-column strip per CTA), 2 = two strips on wide maps
     yield L
     L.set_option("dw_mma", old)
     L.set_option("dw_small", old_small)
+    L.set_option("dw_mma_tws", old_tws)
 
 
 def _operands(N, H, W, C, k, seed=0):
