@@ -59,6 +59,8 @@ int mnb_version(void);
  *   "bn_ctas" (default 0 = sized to the tensor)  CTAs per SM of mnb_bn_bwd_reduce
  *   "dw_small"  (default 1)  whole-tile tensor-pipe depthwise kernels (dw_small.cu) for maps of 12..28 rows (forward,
  *                            backward-data, backward-weight), 2 = every map of at most 28 rows, 0 = never
+ *   "pwb_slice" (default 0)  48 | 80: mnb_pw_bwd_fused also takes Cout = 40 layers whose Cin is a multiple of it, one CTA column
+ *                            per slice of input channels (measured break-even, kept for experiments)
  *   "c3_mma"    (default 1)  bulk-copy + mma.sync kernels for the stride-2 3x3 stage transitions 16->24, 24->40 (forward,
  *                            backward-data, backward-weight) and 40->80 (backward-data) under impl 0 / 3 (c3_mma.cu)
  * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current value or MNB_ERR_ARG. */

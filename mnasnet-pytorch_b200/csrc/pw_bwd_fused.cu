@@ -17,6 +17,8 @@
 //                  the pixel row, is the slow index of both tiles); A_x = relu(s_in*x+t_in) applied to the fragments;
 //                  accumulators stay in registers for the CTA's life
 // and the finished dX rows are staged for the TMA store and reduced against the raw X for the producing block.
+#include <algorithm>
+
 #include "dw_mma.cuh"
 
 namespace mnb {
@@ -68,7 +70,7 @@ template <int CO, int CI>
 struct PwbCfg {
     static constexpr int NCO = CO / 8, NCI = CI / 8;
     // a thread keeps one 8-channel chunk of the (G, Z) tile for life: THREADS is a multiple of 32 and of NCO
-    static constexpr int THREADS = (NCO == 9) ? 288 : ((NCO == 5) ? 160 : 192);
+    static constexpr int THREADS = (NCO == 9) ? 288 : ((NCO == 5) ? 160 : 96);
     static constexpr int WARPS = THREADS / 32;
     static constexpr int R = 16 * WARPS;                    // rows per tile
     static constexpr int KS16 = CO / 16, KS8 = (CO % 16) / 8;     // backward-data k-steps (k = Cout)
@@ -375,7 +377,7 @@ static int launch_pwb(const PwbP& p0, const void* G, const void* Z, const void* 
         occ = o;
     }
     const long long ntiles = (p.M + Cfg::R - 1) / Cfg::R;
-    long long grid = ((long long)num_sms() * occ + slices - 1) / slices;
+    long long grid = std::max(1LL, (long long)num_sms() * occ / slices);      // resident CTAs only (no second wave)
     if (grid > ntiles) grid = ntiles;
     pw_bwd_fused_k<CO, CI><<<dim3((unsigned)grid, (unsigned)slices), Cfg::THREADS, Cfg::SMEM, st>>>(tm_g, tm_z, tm_x, tm_add,
                                                                                                   tm_dx, p);
@@ -398,9 +400,12 @@ int pw_bwd_fused(const void* G, const void* Z, const float* scale, const float* 
     MNB_PWB(72, 24);
     MNB_PWB(24, 72);
 #undef MNB_PWB
-    // (Input-channel slicing -- launch_pwb<CO, CIS> with Cin / CIS CTA columns -- was measured for 72 -> 24, 240 -> 40 and
-    // 480 -> 80: every slice repeats the dZ transform of the G / Z tile, which is the dominant instruction cost, and it
-    // lost to the unfused chain (272 vs 176 us at 28x28 240 -> 40).  Wide layers need the Cout / Cin split over warps.)
+    // wide inputs: CTA columns (blockIdx.y) own slices of CIS input channels; every slice repeats the dZ transform of the
+    // narrow G / Z tile and the 210-255 registers per thread leave one CTA per SM: 174 / 169 us (slices of 48 / 80) against
+    // 180 us for the unfused chain at 28x28 240 -> 40 (scripts/exp_pw_bwd.py slice) -- not a win, so it stays behind the
+    // "pwb_slice" option (default 0).  Wide layers need the Cout / Cin split over warps.
+    if (Cout == 40 && Cin % 48 == 0 && option_get(OPT_PWB_SLICE) == 48) return launch_pwb<40, 48>(p, G, Z, X, add, dX, Cin, st);
+    if (Cout == 40 && Cin % 80 == 0 && option_get(OPT_PWB_SLICE) == 80) return launch_pwb<40, 80>(p, G, Z, X, add, dX, Cin, st);
     set_error("pw_bwd_fused: shape %d -> %d not instantiated", Cin, Cout);
     return MNB_ERR_UNSUPPORTED;
 }

@@ -106,6 +106,14 @@ def main():
             except Exception as e: r = {"shape": f"{hw} {cin}->{cout}", "ok": False, "error": repr(e)[:300]}
             print(json.dumps(r), flush=True); allok = allok and r["ok"]
             if "error" in r: break
+    if "slice" in what:
+        for sl in (48, 80):
+            L.set_option("pwb_slice", sl)
+            try: r = case(256, 28, 28, 240, 40, True, False, timing=True)
+            except Exception as e: r = {"shape": "28 240->40", "ok": False, "error": repr(e)[:300]}
+            r["slice"] = sl
+            print(json.dumps(r), flush=True)
+        L.set_option("pwb_slice", 0)
     print("EXP_PW_BWD", "PASS" if allok else "FAIL")
     return 0 if allok else 1
 if __name__ == "__main__":
