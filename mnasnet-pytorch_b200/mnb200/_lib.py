@@ -84,9 +84,14 @@ def call(name, *args):
     check(getattr(lib, name)(*args), name)
 
 
+OPTION_EPOCH = 0        # bumped by set_option: captured CUDA graphs of a launch program are only valid within one epoch
+
+
 def set_option(name: str, value: int):
     """Process-wide kernel-selection switch ("pw_stream", "stem_mma", "dw_stream"; include/mnb200.h)."""
+    global OPTION_EPOCH
     check(lib.mnb_set_option(name.encode(), int(value)), "set_option")
+    OPTION_EPOCH += 1
 
 
 def get_option(name: str) -> int:

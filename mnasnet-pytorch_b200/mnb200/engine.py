@@ -193,6 +193,8 @@ class Plan:
         self.apps: List[_ConvApp] = []
         self.tape = []
         self.generation = 0
+        self.prog_graphs = {}          # CUDA graphs of the module-path programs (run_graphed)
+        self.static_in = None
         self.last_write = {}
         self.packed = {}
         self.n_events = 0
@@ -699,6 +701,36 @@ class Plan:
         op.detail = getattr(self, "_cur_detail", "")
         ops.append(op)
 
+    def run_graphed(self, ops, pre=None):
+        """Runs a launch program (forward or backward of the module path) through a CUDA graph: the first call of a
+        program runs eagerly (warm-up, lazy module loading), the second captures it, later calls replay.  Every operand
+        of the program lives at a static address (plan buffers, the engine's flat parameter / gradient stores, the
+        static input copy), device-side counters carry the dropout seed, so a replay is the same work as the eager loop
+        minus ~200 Python / ctypes launches -- at 14x14 / 7x7 the kernels are shorter than a launch and the GPU starved.
+        Graphs are keyed by the program list, the dropout state and the kernel-option epoch (a rebuilt program or a
+        changed option recaptures).  `pre` = in-place zeroing that belongs to the program."""
+        key = (id(ops), pre is not None, getattr(self, "dropout_active", False), getattr(self, "masks_injected", False),
+               _lib.OPTION_EPOCH)
+        ent = self.prog_graphs.get(key)
+        stream = torch.cuda.current_stream().cuda_stream
+        if ent is None:                       # first call: eager
+            if len(self.prog_graphs) > 16:
+                self.prog_graphs.clear()
+            self.prog_graphs[key] = "warm"
+            if pre is not None:
+                pre()
+            self.run(ops, stream)
+            return
+        if ent == "warm":                     # second call: capture, then replay
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if pre is not None:
+                    pre()
+                self.run(ops, torch.cuda.current_stream().cuda_stream)
+            self.prog_graphs[key] = ent = (g, ops)      # holds the list: its id cannot be recycled while the graph lives
+        ent[0].replay()
+
     def run(self, ops, stream, after_op=None):
         prof = self.eng.profile
         if prof is None:
@@ -879,6 +911,8 @@ class Engine:
         self.world_size = 1
         self.wgrad_slack = 4           # extra scratch buffers = how far weight-gradient kernels may trail
         self.side_stream = torch.cuda.Stream(device=self.device)
+        # module path (model(x) / loss.backward()): replay the forward / backward programs as CUDA graphs (MNB_MODULE_GRAPHS=0: eager)
+        self.module_graphs = os.environ.get("MNB_MODULE_GRAPHS", "1") != "0"
         self.fuse_bn_reduce = False    # BN-backward reductions in the producing dgrad epilogue (tested; off:
                                        # the dgrad epilogues are the bottleneck, the separate kernel is faster)
         # fused depthwise ConvBlock backward (csrc/dw_mma.cu): 0 off, 1 where it wins, 2 always (MNB_FUSE_DW_BWD overrides)
@@ -957,7 +991,14 @@ class Engine:
         if sub:
             check(lib.mnb_nchw_f32_to_nhwc(x.data_ptr(), plan.sub_in.data_ptr(), N, H, W, C, plan.code, stream),
                   "nchw_to_nhwc")
-        if train:
+        if train and self._graph_ok() and not sub and dropout_masks is None:
+            if plan.static_in is None or plan.static_in.shape != x.shape or plan.static_in.dtype != x.dtype:
+                plan.static_in = torch.empty_like(x)
+            plan.static_in.copy_(x)             # the program reads its input at a static address
+            plan.cur_input = plan.static_in
+            plan.cur_input_ptr = plan.static_in.data_ptr()
+            plan.run_graphed(plan.fwd, plan.dstats.zero_)
+        elif train:
             plan.dstats.zero_()
             plan.run(plan.fwd, stream)
         else:
@@ -972,13 +1013,22 @@ class Engine:
     def backward(self, plan: Plan, zero_grads: bool = True):
         """Runs the backward program; dlogits (or sub_dout) must already be in place."""
         stream = torch.cuda.current_stream().cuda_stream
+        hook = self.grad_hook
+        if hook is None and self._graph_ok() and getattr(self.module, "_mnb", None) == "net" and not plan.masks_injected:
+            plan.run_graphed(plan.bwd, self.store.grad.zero_ if zero_grads else None)
+            return
         if zero_grads:
             self.store.grad.zero_()
-        hook = self.grad_hook
         if hook is None:
             plan.run(plan.bwd, stream)
         else:
             hook.run_backward(self, plan, stream)
+
+    def _graph_ok(self) -> bool:
+        """Module-path programs replay as CUDA graphs unless profiling, data parallel (the bucket hooks interleave
+        NCCL calls with the launches) or already inside a capture (the fused-step graph)."""
+        return (self.module_graphs and self.profile is None and self.grad_hook is None
+                and not torch.cuda.is_current_stream_capturing())
 
     # ---- fused training step (train.py:433-440 entirely in libmnb200) -----------------------------
     def train_step(self, x, target, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
