@@ -991,7 +991,7 @@ class Engine:
         if sub:
             check(lib.mnb_nchw_f32_to_nhwc(x.data_ptr(), plan.sub_in.data_ptr(), N, H, W, C, plan.code, stream),
                   "nchw_to_nhwc")
-        if train and self._graph_ok() and not sub and dropout_masks is None:
+        if train and self._graph_ok(forward=True) and not sub and dropout_masks is None:
             if plan.static_in is None or plan.static_in.shape != x.shape or plan.static_in.dtype != x.dtype:
                 plan.static_in = torch.empty_like(x)
             plan.static_in.copy_(x)             # the program reads its input at a static address
@@ -1024,10 +1024,11 @@ class Engine:
         else:
             hook.run_backward(self, plan, stream)
 
-    def _graph_ok(self) -> bool:
-        """Module-path programs replay as CUDA graphs unless profiling, data parallel (the bucket hooks interleave
-        NCCL calls with the launches) or already inside a capture (the fused-step graph)."""
-        return (self.module_graphs and self.profile is None and self.grad_hook is None
+    def _graph_ok(self, forward=False) -> bool:
+        """Module-path programs replay as CUDA graphs unless profiling or already inside a capture (the fused-step
+        graph); under data parallel only the forward does (the backward's bucket hooks interleave NCCL calls with the
+        launches)."""
+        return (self.module_graphs and self.profile is None and (forward or self.grad_hook is None)
                 and not torch.cuda.is_current_stream_capturing())
 
     # ---- fused training step (train.py:433-440 entirely in libmnb200) -----------------------------
