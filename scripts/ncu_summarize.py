@@ -19,8 +19,10 @@ for r in rows[1:]:
 launches = list(L.values())
 ops0 = json.load(open(opsf))
 ops = []
-for op in ops0:      # a stride-2 3x3 dgrad is four launches (one per input-position parity class)
-    ops += [op] * (4 if (op[0] == 'conv3x3_dgrad' and 'k3s2' in op[1]) else 1)
+C3_DGRAD = ('16->24', '24->40', '40->80')      # one launch (c3_mma.cu); the tcgen05 path takes four (one per parity class)
+for op in ops0:
+    phases = op[0] == 'conv3x3_dgrad' and 'k3s2' in op[1] and not any(s in op[1] for s in C3_DGRAD)
+    ops += [op] * (4 if phases else 1)
 per = len(ops)
 nsteps = len(launches) // per
 assert len(launches) == nsteps * per, (len(launches), per)
