@@ -1,6 +1,6 @@
 // How long does the per-CTA flush of BatchNorm partial sums take?  Every CTA adds 2*C values to the same 2*C addresses.
 // Variants: fp64 atomics (what the kernels do), fp32 atomics, fp64 atomics on 16 replicated slots.
-//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o ub_atomic ub_atomic.cu && ./ub_atomic
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o build/ub_atomic ub_atomic.cu && ./build/ub_atomic
 #include <cstdio>
 #include <cuda_runtime.h>
 
