@@ -20,9 +20,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (int spin = 0; !done; ++spin) {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1 << 24)) __trap();
+        // suspend-time hint (ns): the thread sleeps in hardware until the phase completes instead of spinning through issue slots
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+        if (spin > (1 << 20)) __trap();
     }
 }
 
