@@ -141,6 +141,17 @@ int mnb_pw_bwd_fused(const void* dA, const void* z, const float* scale, const fl
                      const void* x, const float* in_scale, const float* in_shift, const float* w, const void* add,
                      void* dx, float* dw, double* in_sums, long long M, int Cin, int Cout, double m, int dtype,
                      void* stream);
+/* Backward of a "project" pointwise ConvBlock (wide input, narrow output) AFTER its BatchNorm-backward pass (bf16;
+ * csrc/pw_proj_bwd.cu): from dz (M x Cout, the output of mnb_bn_bwd_apply_fused) one kernel computes
+ *   dx = dz W (+ add)                      M x Cin, `add` = optional residual skip gradient
+ *   dw[Cout][Cin] += dz^T relu(in_scale*x + in_shift)                       (dw may be NULL: frozen weight)
+ *   in_sums[0:Cin] += sum dx', in_sums[Cin:2Cin] += sum dx'*x, dx' = dx * [in_scale*x + in_shift > 0]   (NULL = skip)
+ * i.e. convolution_backward of a 1x1 conv plus the reductions of the next native_batch_norm_backward
+ * (src/models/mnasnet.py:58-62,120-128 under autograd).  Instantiated for Cin -> Cout in {240->40, 480->80, 576->96}
+ * (Cout == 96 | 80 with Cin % 96 == 0, Cout == 40 with Cin % 80 == 0); other shapes return MNB_ERR_UNSUPPORTED. */
+int mnb_pw_proj_bwd(const void* dz, const void* x, const float* in_scale, const float* in_shift, const float* w,
+                    const void* add, void* dx, float* dw, double* in_sums, long long M, int Cin, int Cout, int dtype,
+                    void* stream);
 
 /* ---- BatchNorm2d (train) : mnasnet.py:55,60 ; torch:nn/modules/batchnorm.py:163-178 ----------------------
  * finalize: mean/var from stats over m positions -> scale = gamma/sqrt(var+eps), shift = beta-mean*scale,

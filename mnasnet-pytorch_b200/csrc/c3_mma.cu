@@ -43,9 +43,6 @@ struct C3P {
     uint32_t magic_two;
 };
 
-__host__ __device__ constexpr int c3_odd16(int bytes) { return ((bytes / 16) | 1) * 16; }     // 16-byte multiple x odd: conflict-free ldmatrix rows
-__host__ __device__ constexpr int c3_al128(int bytes) { return (bytes + 127) / 128 * 128; }
-
 template <int CIN, int COUT>
 struct C3Cfg {
     static constexpr int WARPS = 7, THREADS = 32 * WARPS, MTW = 2, PTMAX = 16 * MTW * WARPS;
@@ -112,22 +109,6 @@ __device__ __forceinline__ void c3_load_weights(unsigned char* ws, const C3P& p,
             *reinterpret_cast<bf16*>(ws + r * WP + k * 2) = __float2bfloat16_rn(p.w[((size_t)co * cin + ci) * 9 + tap]);
         }
     }
-}
-
-// B fragments of NT n-tiles for one k16 / k8 step at byte offset kb inside the weight rows
-template <int NT, int WP>
-__device__ __forceinline__ void c3_load_b16(uint32_t (&b)[NT][2], uint32_t b4, uint32_t b2, int kb) {
-#pragma unroll
-    for (int jp = 0; jp < NT / 2; ++jp) ldsm4(b4 + jp * 16 * WP + kb, b[2 * jp][0], b[2 * jp][1], b[2 * jp + 1][0], b[2 * jp + 1][1]);
-    if constexpr (NT & 1) ldsm2(b2 + kb, b[NT - 1][0], b[NT - 1][1]);
-}
-template <int NT, int WP>
-__device__ __forceinline__ void c3_load_b8(uint32_t (&b)[NT][2], uint32_t b8, int kb) {
-#pragma unroll
-    for (int q = 0; q < NT / 4; ++q) ldsm4(b8 + q * 32 * WP + kb, b[4 * q][0], b[4 * q + 1][0], b[4 * q + 2][0], b[4 * q + 3][0]);
-    constexpr int R = NT & 3, Q = NT / 4 * 4;
-    if constexpr (R >= 2) ldsm2(b8 + Q * 8 * WP + kb, b[Q][0], b[Q + 1][0]);
-    if constexpr (R & 1) ldsm1(b8 + (NT - 1) * 8 * WP + kb, b[NT - 1][0]);
 }
 
 // one tap of the implicit GEMM: acc[i][j] += A_i (K = KC channels at abase[i]) * B_j (weight rows at byte offset kb0)

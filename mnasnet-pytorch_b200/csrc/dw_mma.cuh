@@ -109,6 +109,26 @@ __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 
 // exact floor(n / d) for n < 65536 and d < 65536: q = (n * magic) >> 32, magic = floor(2^32 / d) + 1
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t magic) { return __umulhi(n, magic); }
 
+// ---- dense-GEMM helpers shared by c3_mma.cu / pw_proj_bwd.cu: weight rows [n][K] in shared memory, pitch 16 B x odd ----
+__host__ __device__ constexpr int c3_odd16(int bytes) { return ((bytes / 16) | 1) * 16; }     // 16-byte multiple x odd: conflict-free ldmatrix rows
+__host__ __device__ constexpr int c3_al128(int bytes) { return (bytes + 127) / 128 * 128; }
+
+// B fragments of NT n-tiles for one k16 / k8 step at byte offset kb inside the weight rows
+template <int NT, int WP>
+__device__ __forceinline__ void c3_load_b16(uint32_t (&b)[NT][2], uint32_t b4, uint32_t b2, int kb) {
+#pragma unroll
+    for (int jp = 0; jp < NT / 2; ++jp) ldsm4(b4 + jp * 16 * WP + kb, b[2 * jp][0], b[2 * jp][1], b[2 * jp + 1][0], b[2 * jp + 1][1]);
+    if constexpr (NT & 1) ldsm2(b2 + kb, b[NT - 1][0], b[NT - 1][1]);
+}
+template <int NT, int WP>
+__device__ __forceinline__ void c3_load_b8(uint32_t (&b)[NT][2], uint32_t b8, int kb) {
+#pragma unroll
+    for (int q = 0; q < NT / 4; ++q) ldsm4(b8 + q * 32 * WP + kb, b[4 * q][0], b[4 * q + 1][0], b[4 * q + 2][0], b[4 * q + 3][0]);
+    constexpr int R = NT & 3, Q = NT / 4 * 4;
+    if constexpr (R >= 2) ldsm2(b8 + Q * 8 * WP + kb, b[Q][0], b[Q + 1][0]);
+    if constexpr (R & 1) ldsm1(b8 + (NT - 1) * 8 * WP + kb, b[NT - 1][0]);
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------------------------
 // 4-D map of an NHWC bf16 tensor with box {bc channels, bw columns, bh rows, 1 image}; cached per (pointer, shape,
 // box) -- the engine's buffers are static, so every map is encoded once per plan.

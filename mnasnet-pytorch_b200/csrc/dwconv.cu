@@ -312,6 +312,8 @@ int dw_bwd_small(const void* G, const void* Z, const float* scale, const float* 
                  const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
                  const float* in_scale, const float* in_shift, const float* w, void* dX, float* dw, double* nsums, int N, int H,
                  int W, int C, int k, cudaStream_t st);
+int pw_proj_bwd(const void* dz, const void* x, const float* in_scale, const float* in_shift, const float* w, const void* add,
+                void* dx, float* dw, double* nsums, long long M, int Cin, int Cout, cudaStream_t st);
 int pw_bwd_fused(const void* G, const void* Z, const float* scale, const float* shift, const double* sums, const float* mean,
                  const float* invstd, double m, float* dgamma, float* dbeta, float* dbias, const void* X,
                  const float* in_scale, const float* in_shift, const float* w, const void* add, void* dX, float* dw,
@@ -457,6 +459,17 @@ int mnb_pw_bwd_fused(const void* dA, const void* z, const float* scale, const fl
     if (dtype != MNB_BF16) { set_error("pw_bwd_fused: bf16 only"); return MNB_ERR_UNSUPPORTED; }
     return pw_bwd_fused(dA, z, scale, shift, sums, save_mean, save_invstd, m, dgamma, dbeta, dbias, x, in_scale, in_shift, w,
                         add, dx, dw, in_sums, M, Cin, Cout, (cudaStream_t)stream);
+}
+
+int mnb_pw_proj_bwd(const void* dz, const void* x, const float* in_scale, const float* in_shift, const float* w,
+                    const void* add, void* dx, float* dw, double* in_sums, long long M, int Cin, int Cout, int dtype,
+                    void* stream) {
+    MNB_REQUIRE(M > 0 && Cin > 0 && Cout > 0 && Cin % 8 == 0 && Cout % 8 == 0, "pw_proj_bwd: bad M / Cin / Cout");
+    MNB_REQUIRE(dz && x && w && dx, "pw_proj_bwd: NULL operand");
+    MNB_REQUIRE(!in_sums || in_scale, "pw_proj_bwd: in_sums needs in_scale / in_shift");
+    MNB_REQUIRE(!in_scale || in_shift, "pw_proj_bwd: in_scale without in_shift");
+    if (dtype != MNB_BF16) { set_error("pw_proj_bwd: bf16 only"); return MNB_ERR_UNSUPPORTED; }
+    return pw_proj_bwd(dz, x, in_scale, in_shift, w, add, dx, dw, in_sums, M, Cin, Cout, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -593,6 +593,22 @@ class Plan:
                 if not in_held:
                     free.append(gbuf)
                 r = a.inp
+                if self._proj_pw_backward(a, idx, first_live):
+                    # project 1x1 block (wide -> narrow): backward-data (+ skip gradient) + backward-weight + the
+                    # BN-backward reductions of the block that produced its input in one kernel (csrc/pw_proj_bwd.cu)
+                    pa = self.apps[a.index - 1] if (a.index > 0 and r.scale is not None and
+                                                    self.apps[a.index - 1].z is r.t) else None
+                    dx = take()
+                    add = held[-1] if (idx > 0 and self.tape[idx - 1][0] == "res_begin") else None
+                    self._op(ops, "mnb_pw_proj_bwd", dz, r.t, r.scale, r.shift, conv.weight, add, dx, Gp(conv.weight),
+                             pa.sums if pa is not None else None, r.M, r.C, C, self.code,
+                             nbytes=a.out_bytes + a.in_bytes * (3 if add is not None else 2),
+                             label=a.label + "_bwd_proj")
+                    if pa is not None:
+                        pa.reduce_fused = True
+                    free.append(dz)
+                    gbuf = dx
+                    continue
                 x_t = r.t if not r.nchw else _InputPtr(self)
                 layout = a.in_layout
                 wg = rg(conv.weight)
@@ -675,6 +691,17 @@ class Plan:
         if a.inp.nchw or not (a.need_dgrad and idx > first_live):
             return False
         return (a.inp.C, a.Cout) in self.PW_FUSED_SHAPES
+
+    def _proj_pw_backward(self, a, idx, first_live) -> bool:
+        """Where the fused project-block backward (after the BN pass) is used: bf16 1x1 blocks 240->40, 480->80, 576->96
+        (the shapes csrc/pw_proj_bwd.cu is instantiated for) whose data gradient is needed."""
+        eng = self.eng
+        if eng.dtype != "bf16" or not eng.fuse_proj_bwd or a.kind != "dense" or a.k != 1 or a.stride != 1:
+            return False
+        if a.inp.nchw or not (a.need_dgrad and idx > first_live):
+            return False
+        cin, cout = a.inp.C, a.Cout
+        return (cout in (96, 80) and cin % 96 == 0 and cin >= 4 * cout) or (cout == 40 and cin % 80 == 0 and cin >= 4 * cout)
 
     def _new_event(self):
         self.n_events += 1
@@ -918,6 +945,7 @@ class Engine:
         # fused depthwise ConvBlock backward (csrc/dw_mma.cu): 0 off, 1 where it wins, 2 always (MNB_FUSE_DW_BWD overrides)
         self.fuse_dw_bwd = int(os.environ.get("MNB_FUSE_DW_BWD", "1"))
         self.fuse_pw_bwd = 1           # fused pointwise ConvBlock backward (csrc/pw_bwd_fused.cu) for its shapes
+        self.fuse_proj_bwd = int(os.environ.get("MNB_FUSE_PROJ_BWD", "1"))   # project blocks: dgrad + wgrad + producer reduction (csrc/pw_proj_bwd.cu)
         self.profile = None            # list -> Plan.run records (label, bytes, ev0, ev1) per launch
         self.optimizer = "adam"        # 'adam' | 'rmsprop' | 'sgd' (train.py:218-231); set before the first graph capture
 

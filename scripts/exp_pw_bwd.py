@@ -116,5 +116,31 @@ def main():
         L.set_option("pwb_slice", 0)
     print("EXP_PW_BWD", "PASS" if allok else "FAIL")
     return 0 if allok else 1
-if __name__ == "__main__":
+if __name__ == "__main__" and "proj" not in sys.argv[1:]:
     sys.exit(main())
+
+
+def proj_timing(H, Cin, Cout, add=True, N=256):
+    """mnb_pw_proj_bwd vs conv_dgrad + conv_wgrad + bn_bwd_reduce(producer) on the same dZ."""
+    M = N * H * H
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dz = torch.randn(M, Cout, device="cuda", generator=g).to(BF)
+    x = torch.randn(M, Cin, device="cuda", generator=g).to(BF)
+    sk = torch.randn(M, Cin, device="cuda", generator=g).to(BF) if add else None
+    w = (torch.randn(Cout, Cin, 1, 1, device="cuda", generator=g) / Cin ** 0.5).float()
+    isc = (torch.rand(Cin, device="cuda", generator=g) + 0.5).float(); ish = (torch.randn(Cin, device="cuda", generator=g) * 0.3).float()
+    dx = torch.empty_like(x); dw = torch.zeros_like(w); ns = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
+    wpk_d = torch.empty(w.numel(), device="cuda", dtype=BF); wpk_f = torch.empty(w.numel(), device="cuda", dtype=BF)
+    L.call("mnb_pack_weights", P(w), P(wpk_f), P(wpk_d), Cout, Cin, 1, S())
+    def unfused():
+        L.call("mnb_conv_dgrad_packed", P(dz), P(w), P(wpk_d), P(sk), P(dx), None, None, None, None, N, H, H, Cin, Cout, 1, 1, 0, 1, 0, S())
+        L.call("mnb_conv_wgrad", P(x), P(isc), P(ish), P(dz), P(dw), N, H, H, Cin, Cout, 1, 1, 0, 1, 0, 0, S())
+        L.call("mnb_bn_bwd_reduce", P(dx), P(x), P(isc), P(ish), P(ns), M, Cin, 1, S())
+    def fused():
+        L.call("mnb_pw_proj_bwd", P(dz), P(x), P(isc), P(ish), P(w), P(sk), P(dx), P(dw), P(ns), M, Cin, Cout, 1, S())
+    print(json.dumps({"shape": f"{N}x{H}x{H} {Cin}->{Cout}", "add": add, "unfused_us": round(timeit(unfused), 1), "proj_fused_us": round(timeit(fused), 1)}), flush=True)
+
+
+if __name__ == "__main__" and "proj" in sys.argv[1:]:
+    for (H, ci, co) in ((14, 576, 96), (28, 240, 40), (14, 480, 80)):
+        proj_timing(H, ci, co)
