@@ -19,11 +19,19 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 python scripts/ncu_summarize.py gpurun_out/ncu_raw.csv gpurun_out/ops.json r2 gpurun_out > gpurun_out/ncu_summarize.log 2>&1 || tail -3 gpurun_out/ncu_summarize.log
 rm -f gpurun_out/ncu_raw.csv
 echo "== ncu --set full of ~50 GEMM / depthwise / fused launches of the timed step -> summary JSON (the .ncu-rep stays on the box) =="
-timeout 900 ncu --set full --clock-control none -k 'regex:conv_tc_k|pw_stream_k|pw_wgrad_stream_k|dw_mma|dws_|c3_|stem_fwd_mma|pw_bwd_fused|dw_tile_k' \
+timeout 900 ncu --set full --clock-control none -k 'regex:conv_tc_k|pw_stream_k|pw_wgrad_stream_k|dw_mma|dws_|c3_|stem_fwd_mma|pw_bwd_fused|pw_proj_bwd|dw_tile_k' \
     --launch-skip 700 --launch-count 90 -o /tmp/r2_ncu_step_gemm_dw -f \
     python bench.py --steps 3 --warmup 3 --no-graph --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 python scripts/ncu_summary.py /tmp/r2_ncu_step_gemm_dw.ncu-rep gpurun_out/r2_ncu_gemm_dw_summary.json > /dev/null 2>&1
+echo "== stand-alone kernel experiments (parity + timing against the kernels they replace) =="
+timeout 300 python scripts/exp_c3.py > gpurun_out/r2_exp_c3.txt 2>&1; tail -4 gpurun_out/r2_exp_c3.txt | cut -c1-200
+timeout 300 python scripts/exp_dw_small.py parity time bwd > gpurun_out/r2_exp_dw_small.txt 2>&1; tail -3 gpurun_out/r2_exp_dw_small.txt | cut -c1-200
+timeout 300 python scripts/exp_pw_bwd.py proj > gpurun_out/r2_exp_pw_proj.txt 2>&1; cat gpurun_out/r2_exp_pw_proj.txt | cut -c1-200
+timeout 300 python scripts/exp_pw_bwd.py time > gpurun_out/r2_exp_pw_bwd_time.txt 2>&1; tail -2 gpurun_out/r2_exp_pw_bwd_time.txt | cut -c1-200
+timeout 100 ./scripts/ubench/build/ub_atomic > gpurun_out/r2_ubench_atomic.txt 2>&1
+echo "== smoke =="
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.txt 2>&1; tail -2 gpurun_out/r2_smoke.txt
 find gpurun_out -size +20M -delete
 du -sh gpurun_out
 echo done
