@@ -61,6 +61,8 @@ int mnb_version(void);
  *                            backward-data, backward-weight), 2 = every map of at most 28 rows, 0 = never
  *   "pwb_slice" (default 0)  48 | 80: mnb_pw_bwd_fused also takes Cout = 40 layers whose Cin is a multiple of it, one CTA column
  *                            per slice of input channels (measured break-even, kept for experiments)
+ *   "pw_wide"   (default 0)  1 = cp.async + mma.sync forward (pw_wide_fwd.cu) for the wide 1x1 layers 40<->240, 80<->480,
+ *                            96<->576 under impl 0 / 3 (measured 15-35 % slower than the tcgen05 pipeline: kept for experiments)
  *   "c3_mma"    (default 1)  bulk-copy + mma.sync kernels for the stride-2 3x3 stage transitions 16->24, 24->40 (forward,
  *                            backward-data, backward-weight) and 40->80 (backward-data) under impl 0 / 3 (c3_mma.cu)
  * mnb_set_option returns 0 or MNB_ERR_ARG (unknown name); mnb_get_option the current value or MNB_ERR_ARG. */

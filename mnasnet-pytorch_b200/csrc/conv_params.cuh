@@ -46,4 +46,7 @@ int conv_fwd_c3(const ConvP& p, cudaStream_t st);
 int conv_dgrad_c3(const ConvP& p, cudaStream_t st);
 int conv_wgrad_c3(const ConvP& p, cudaStream_t st);
 
+// cp.async + mma.sync forward for the wide 1x1 layers of the 28x28 / 14x14 stages (pw_wide_fwd.cu); MNB_ERR_UNSUPPORTED otherwise
+int conv_fwd_pwide(const ConvP& p, cudaStream_t st);
+
 }  // namespace mnb

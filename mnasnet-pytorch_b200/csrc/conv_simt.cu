@@ -403,6 +403,8 @@ int mnb_conv_fwd_packed(const void* x, const float* in_scale, const float* in_sh
     if (dtype == MNB_BF16 && (impl == 0 || impl == 3)) {
         int r = conv_fwd_c3(p, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;
+        r = conv_fwd_pwide(p, (cudaStream_t)stream);
+        if (r != MNB_ERR_UNSUPPORTED) return r;
     }
     if (impl != 1 && dtype == MNB_BF16) {
         int r = conv_fwd_tc(p, (cudaStream_t)stream);
