@@ -57,8 +57,9 @@ int mnb_version(void);
  *   "dw_mma_cg" / "dw_mma_tws" / "dw_mma_seg" (default 0 = automatic)  geometry overrides of those kernels: channels per
  *                            CTA (24 | 40), 16-column strips per CTA (1 | 2), row blocks per work item
  *   "bn_ctas" (default 0 = sized to the tensor)  CTAs per SM of mnb_bn_bwd_reduce
- *   "dw_small"  (default 1)  whole-tile tensor-pipe depthwise kernels (dw_small.cu) for maps of 12..28 rows (forward,
- *                            backward-data, backward-weight), 2 = every map of at most 28 rows, 0 = never
+ *   "dw_small"  (default 1)  whole-tile tensor-pipe depthwise kernels (dw_small.cu): forward, backward-data and backward-weight
+ *                            on maps of 12..64 rows, the fused backward on every map of >= 12 rows (5x5: up to 64 rows);
+ *                            2 = every shape, 0 = never (row-streaming / tile kernels)
  *   "pwb_slice" (default 0)  48 | 80: mnb_pw_bwd_fused also takes Cout = 40 layers whose Cin is a multiple of it, one CTA column
  *                            per slice of input channels (measured break-even, kept for experiments)
  *   "pw_wide"   (default 0)  1 = cp.async + mma.sync forward (pw_wide_fwd.cu) for the wide 1x1 layers 40<->240, 80<->480,

@@ -1,4 +1,4 @@
-// Depthwise k x k (3 / 5) stride-1 convolution on SMALL maps (H <= 28), bf16 NHWC, on the tensor pipe: forward (+ the
+// Depthwise k x k (3 / 5) stride-1 convolution in WHOLE TILES (written for the small maps, H <= 28), bf16 NHWC, on the tensor pipe: forward (+ the
 // producing ConvBlock's BN-apply+ReLU on load, + BN batch statistics on store), backward-data and backward-weight.
 // Same math and entry points as dw_mma.cu (nn.Conv2d(groups=C) at src/models/mnasnet.py:76-81,120-125); same MMA
 // formulation (m16n8k16 with a diagonal B per 8-channel chunk, A straight from the NHWC tile through ldmatrix).
@@ -10,7 +10,9 @@
 // WHOLE tile of TH = 14 output rows: one TMA box brings the TH + k - 1 input rows (halo rows / columns outside the image
 // are zero-filled by the hardware), the row loop is fully unrolled with the tile-edge taps dropped at compile time (no
 // prologue, no range checks, nothing recomputed but the in-place transform of the halo rows), one TMA store writes the
-// TH x TW output box.  14 x 14 maps are one item per (image, channel group), 28 x 28 two.
+// TH x TW output box.  14 x 14 maps are one item per (image, channel group), 28 x 28 two.  Measured afterwards: the same
+// kernels also beat the row-streaming ones on the 56 x 56 maps, and the fused backward does on 112 x 112 (14.85 -> 14.25 ms
+// per step), so the default policy (dw_small_covers / dw_small_covers_bwd) takes those too.
 #include "dw_mma_dev.cuh"
 
 namespace mnb {
@@ -714,11 +716,18 @@ static int dws_launch_wgrad(const DwmGeom& g, const void* x, const float* s, con
 }
 
 // maps of at most 28 rows; the channel-group / strip geometry is dw_mma's (24 | 40 channels, 1 | 2 strips of 16 columns)
-// option "dw_small": 1 = maps of 12..28 rows (the 28 x 28 and 14 x 14 stages), 2 = every map of at most 28 rows, 0 = never
+// option "dw_small": 1 = where the whole-tile kernels measured faster than the row-streaming ones -- forward / backward-data /
+// backward-weight on maps of 12..64 rows, the fused backward on every map of >= 12 rows (5x5 up to 64 rows); 2 = every
+// shape (tests); 0 = never
 bool dw_small_covers(int H, int W, int C, int k) {
     const int o = option_get(OPT_DW_SMALL);
-    if (!o || (k != 3 && k != 5) || H > 28 || C % 8 != 0) return false;
-    return o == 2 || (H >= 12 && W >= 12);
+    if (!o || (k != 3 && k != 5) || C % 8 != 0) return false;
+    return o == 2 || (H >= 12 && H <= 64 && W >= 12);
+}
+bool dw_small_covers_bwd(int H, int W, int C, int k) {
+    const int o = option_get(OPT_DW_SMALL);
+    if (!o || (k != 3 && k != 5) || C % 8 != 0) return false;
+    return o == 2 || (H >= 12 && W >= 12 && (k == 3 || H <= 64));
 }
 
 #define DWS_DISPATCH(CALL)                                                    \

@@ -303,6 +303,7 @@ int dw_wgrad_mma(const void* x, const float* s, const float* t, const void* dz, 
                  cudaStream_t st);
 // whole-tile variants for maps of at most 28 rows (dw_small.cu), option "dw_small"
 bool dw_small_covers(int H, int W, int C, int k);
+bool dw_small_covers_bwd(int H, int W, int C, int k);
 int dw_fwd_small(const void* x, const float* s, const float* t, const float* w, void* z, double* stats, int N, int H, int W,
                  int C, int k, cudaStream_t st);
 int dw_dgrad_small(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
@@ -437,7 +438,7 @@ int mnb_dw_bwd_fused(const void* dA, const void* z, const float* scale, const fl
     MNB_REQUIRE(!in_scale || in_shift, "dw_bwd_fused: in_scale without in_shift");
     MNB_REQUIRE(m > 0, "dw_bwd_fused: bad element count");
     if (dtype != MNB_BF16) { set_error("dw_bwd_fused: bf16 only"); return MNB_ERR_UNSUPPORTED; }
-    if (dw_small_covers(H, W, C, k)) {
+    if (dw_small_covers_bwd(H, W, C, k)) {
         int r = dw_bwd_small(dA, z, scale, shift, sums, save_mean, save_invstd, m, dgamma, dbeta, dbias, x, in_scale, in_shift,
                              w, dx, dw, in_sums, N, H, W, C, k, (cudaStream_t)stream);
         if (r != MNB_ERR_UNSUPPORTED) return r;

@@ -664,8 +664,10 @@ class Plan:
         """Where the fused depthwise backward kernels are used (bf16; the input must come straight from a ConvBlock: raw z
         + scale / shift) -- the layers where they measured faster than the unfused chain: the row-streaming kernel
         (dw_mma.cu) for 3x3 on maps of >= 56 rows with a channel count the 24-channel geometry tiles exactly
-        (profiles/r2_exp_dw_mma.json), the whole-tile kernel (dw_small.cu) on the 28 x 28 and 14 x 14 maps
-        (scripts/exp_dw_small.py bwd: 242 vs 277, 148 vs 172, 76 vs 136 us)."""
+        (profiles/r2_exp_dw_mma.json) when the whole-tile kernels are switched off; by default the whole-tile kernel
+        (dw_small.cu) on every map of >= 12 rows (5x5 up to 64 rows): 242 vs 277, 148 vs 172, 76 vs 136 us on the 28 x 28 /
+        14 x 14 blocks (scripts/exp_dw_small.py bwd), and 14.85 -> 14.25 ms per step from the 56 x 56 5x5 and 112 x 112 3x3
+        blocks."""
         eng = self.eng
         if eng.dtype != "bf16" or not eng.fuse_dw_bwd or a.kind != "dw":
             return False
@@ -676,8 +678,8 @@ class Plan:
             return False
         if eng.fuse_dw_bwd == 2:                 # forced (tests): every shape the kernel supports
             return r.H >= 1
-        if 12 <= r.H <= 28 and r.W >= 12 and _lib.get_option("dw_small") == 1:
-            return True
+        if _lib.get_option("dw_small") == 1:      # whole-tile fused kernel (dw_small.cu): every map it is dispatched for
+            return r.H >= 12 and r.W >= 12 and (a.k == 3 or r.H <= 64)
         return a.k == 3 and r.H >= 56 and r.W >= 24 and a.Cout % 24 == 0
 
     PW_FUSED_SHAPES = {(16, 48), (48, 16), (32, 16), (24, 72), (72, 24)}       # (Cin, Cout) instantiated in pw_bwd_fused.cu

@@ -1,7 +1,7 @@
 """GPU: the whole-tile depthwise kernels for small maps (csrc/dw_small.cu) behind mnb_dw_fwd / mnb_dw_dgrad / mnb_dw_wgrad,
 against torch fp32 math on the same bf16 operands: forward + BN statistics of the stored values, backward-data,
-backward-weight.  Option dw_small = 2 routes every map of at most 28 rows there (default 1: 12..28 rows, the 28 x 28 and
-14 x 14 stages of MnasNet: nn.Conv2d(groups=C) at src/models/mnasnet.py:76-81,120-125).  Shapes: one and two row tiles,
+backward-weight.  Option dw_small = 2 routes every shape there (default 1: maps of 12..64 rows, the 56 x 56 .. 14 x 14
+stages of MnasNet: nn.Conv2d(groups=C) at src/models/mnasnet.py:76-81,120-125).  Shapes: one and two row tiles,
 ragged heights / widths, one and two 16-column strips, 24- and 40-channel groups with partial last groups, 7 x 7 and 4 x 4
 maps (TH = 7 tiles), with / without the fused BN-apply+ReLU of the producing block.  Gate 1e-2 rel-L2, statistics 1e-5."""
 import pytest
@@ -30,7 +30,8 @@ def forced_small():
 
 CASES = [(3, 14, 14, 48, 5), (3, 14, 14, 48, 3), (2, 28, 28, 72, 5), (2, 28, 28, 40, 3), (2, 7, 7, 96, 5), (2, 7, 7, 48, 3),
          (2, 16, 24, 32, 5), (2, 12, 16, 56, 3), (2, 24, 32, 24, 5), (3, 4, 4, 80, 5), (2, 28, 20, 240, 5), (2, 14, 14, 576, 5),
-         (2, 14, 14, 480, 3), (2, 20, 20, 88, 3), (1, 6, 8, 1152, 3), (2, 27, 17, 16, 5), (2, 15, 33, 8, 3)]
+         (2, 14, 14, 480, 3), (2, 20, 20, 88, 3), (1, 6, 8, 1152, 3), (2, 27, 17, 16, 5), (2, 15, 33, 8, 3),
+         (2, 56, 56, 72, 5), (1, 112, 112, 48, 3), (1, 40, 64, 24, 5), (1, 64, 48, 32, 3), (1, 113, 50, 16, 3)]
 
 
 @pytest.mark.parametrize("act", [True, False])
