@@ -23,7 +23,7 @@ for name, f in rows:
     d = line(f)
     e = d.get("e2e") or {}
     c = d.get("clocks") or {}
-    out.append(f"| {name} | {d['value']:.0f} | {d['ms_per_step']:.2f} | {e.get('value', 0):.0f} | {c.get('sm_mhz', 0):.0f} MHz, reasons {c.get('reasons', [])} | `{f}` |")
+    out.append(f"| {name} | {d['value']:.0f} | {d['ms_per_step']:.2f} | {(e.get('value') or 0):.0f} | {(c.get('sm_mhz') or 0):.0f} MHz, reasons {c.get('reasons', [])} | `{f}` |")
 ref = line("r2_bench_reference_arm.json")
 ge = b1.get("gpu_eager_baseline") or {}
 cb = b1.get("cpu_baseline") or {}
