@@ -12,7 +12,8 @@ def line(f):
 out = []
 b1 = line("r2_bench_1gpu.json")
 rows = [("1 GPU, 224x224, batch 256 (BASELINE configs[1])", "r2_bench_1gpu.json"), ("2 GPUs (NCCL, weak scaling)", "r2_bench_2gpu.json"),
-        ("8 GPUs (NCCL, weak scaling)", "r2_bench_8gpu.json"),
+        ("4 GPUs (NCCL, weak scaling)", "r2_bench_4gpu.json"),
+        ("8 GPUs (NCCL, weak scaling; measured one kernel-policy change earlier, at 14.9 ms/step on one GPU)", "r2_bench_8gpu.json"),
         ("1 GPU, 112x112, batch 512 (configs[3])", "r2_bench_cfg3_112_b512.json"), ("1 GPU, 192x256, batch 256 (configs[4])", "r2_bench_cfg4_192x256.json"),
         ("1 GPU, 256x192, batch 256 (configs[4])", "r2_bench_cfg4_256x192.json"),
         ("1 GPU, 224x224, 2048 images per step (configs[2] strong-scaling shard)", "r2_bench_cfg2_strong_2048_1gpu.json")]
