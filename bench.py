@@ -489,7 +489,7 @@ def _kernel_options():
     """Which kernel families `impl` auto selects (mnb_get_option): recorded with every bench line."""
     try:
         from mnb200 import _lib
-        return {n: _lib.get_option(n) for n in ("pw_stream", "stem_mma", "dw_stream", "dw_mma")}
+        return {n: _lib.get_option(n) for n in ("pw_stream", "stem_mma", "dw_mma", "dw_small", "c3_mma")}
     except Exception as e:      # never lose a measurement over a label
         return {"error": str(e)}
 

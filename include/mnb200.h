@@ -44,13 +44,6 @@ int mnb_version(void);
 /* Kernel-selection switches (process-wide; an unset option takes MNB_<NAME> from the environment, then its default):
  *   "pw_stream" (default 1)  auto routes the low-channel bf16 1x1 layers to the warp-streaming kernels (pw_stream.cu)
  *   "stem_mma"  (default 1)  auto uses the tensor-pipe stem backward-weight kernel in bf16 mode
- *   "dw_stream" (default 0)  bf16 depthwise layers: 0 = shared-memory tile kernels only, 1 = register row-stream
- *                            kernels (dwconv_stream.cu) everywhere, 2 = row-stream where it measured faster
- *                            (forward / backward-data on maps of <= 7 rows and of the 5x5 layers on >= 56 rows)
- *   "dw_stream_pd" (default 1)  input rows the row-stream kernels keep in flight ahead of the one they consume (1..3;
- *                            2 and 3 are untimed experiments: more memory-level parallelism, more registers)
- *   "dw_stream_tw8" (default 0) 3x3 row-stream forward / backward-data with 8 instead of 4 output columns per lane
- *                            (fewer halo loads and per-row overheads per output, more registers; untimed experiment)
  *   "dw_mma" (default 1)     bf16 depthwise layers on the TMA + mma.sync kernels (dw_mma.cu): 1 = where they measured
  *                            faster than the tile kernels (forward / backward-data on maps of >= 12 rows, backward-weight
  *                            when additionally C % 24 == 0), 2 = every shape, 0 = never

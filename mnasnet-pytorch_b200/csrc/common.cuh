@@ -14,10 +14,8 @@ typedef __nv_bfloat16 bf16;
 void set_error(const char* fmt, ...);
 
 // run-time kernel-selection switches (mnb_set_option / environment, see include/mnb200.h)
-enum { OPT_PW_STREAM = 0, OPT_STEM_MMA = 1, OPT_DW_STREAM = 2, OPT_DW_STREAM_PD = 3, OPT_DW_STREAM_TW8 = 4, OPT_DW_MMA = 5,
-       OPT_DW_MMA_CG = 6, OPT_DW_MMA_TWS = 7, OPT_DW_MMA_SEG = 8, OPT_BN_CTAS = 9, OPT_C3_MMA = 10,
-       OPT_DW_SMALL = 11, OPT_PWB_SLICE = 12, OPT_PW_WIDE = 13,
-       OPT_COUNT = 14 };
+enum { OPT_PW_STREAM = 0, OPT_STEM_MMA, OPT_DW_MMA, OPT_DW_MMA_CG, OPT_DW_MMA_TWS, OPT_DW_MMA_SEG, OPT_BN_CTAS, OPT_C3_MMA,
+       OPT_DW_SMALL, OPT_PWB_SLICE, OPT_PW_WIDE, OPT_COUNT };
 int option_get(int id);
 
 #define MNB_REQUIRE(cond, ...)               \

@@ -277,23 +277,6 @@ static int check_dw(const char* name, int N, int H, int W, int C, int k, int dty
 
 using namespace mnb;
 
-// row-stream kernels (dwconv_stream.cu), selected by the "dw_stream" option: 0 = never, 1 = always, 2 = where they
-// measured faster than the tile kernels on B200 (profiles/r1_exp_dw_stream.json): forward and backward-data of
-// 7x7-and-smaller maps and of the 5x5 layers on >= 56-row maps (backward-weight stays on the tile kernels)
-namespace mnb {
-static bool use_dw_stream(int pass /*0 fwd, 1 dgrad, 2 wgrad*/, int H, int k) {
-    const int o = option_get(OPT_DW_STREAM);
-    if (o == 1) return true;
-    if (o != 2) return false;
-    return pass != 2 && (H <= 7 || (k == 5 && H >= 56));
-}
-int dw_fwd_stream(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z,
-                  double* stats, int N, int H, int W, int C, int k, cudaStream_t st);
-int dw_dgrad_stream(const void* dz, const float* w, void* dx, int N, int H, int W, int C, int k, cudaStream_t st);
-int dw_wgrad_stream(const void* x, const float* s, const float* t, const void* dz, float* dw, int N, int H, int W,
-                    int C, int k, cudaStream_t st);
-}  // namespace mnb
-
 // TMA + mma.sync kernels (dw_mma.cu), option "dw_mma" (default 1): bf16 forward / stand-alone backward-data
 namespace mnb {
 int dw_fwd_mma(const void* x, const float* s, const float* t, const float* w, const float* bias, void* z, double* stats,
@@ -336,13 +319,9 @@ int mnb_dw_fwd(const void* x, const float* in_scale, const float* in_shift, cons
         int r = dw_fwd_small(x, in_scale, in_shift, w, z, stats, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
-    if (dtype == MNB_BF16 && !bias && !use_dw_stream(0, H, k) &&
+    if (dtype == MNB_BF16 && !bias &&
         (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12))) {
         int r = dw_fwd_mma(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
-        if (r != MNB_ERR_UNSUPPORTED) return r;
-    }
-    if (dtype == MNB_BF16 && use_dw_stream(0, H, k)) {
-        int r = dw_fwd_stream(x, in_scale, in_shift, w, bias, z, stats, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
     if (dtype == MNB_BF16) {
@@ -370,13 +349,9 @@ int mnb_dw_dgrad(const void* dz, const float* w, void* dx, const void* bn_z, con
         int r = dw_dgrad_small(dz, w, dx, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
-    if (dtype == MNB_BF16 && !bn_z && !use_dw_stream(1, H, k) &&
+    if (dtype == MNB_BF16 && !bn_z &&
         (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12))) {
         int r = dw_dgrad_mma(dz, w, dx, N, H, W, C, k, st);
-        if (r != MNB_ERR_UNSUPPORTED) return r;
-    }
-    if (dtype == MNB_BF16 && !bn_z && use_dw_stream(1, H, k)) {
-        int r = dw_dgrad_stream(dz, w, dx, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
     if (dtype == MNB_BF16) {
@@ -404,13 +379,9 @@ int mnb_dw_wgrad(const void* x, const float* in_scale, const float* in_shift, co
         int r = dw_wgrad_small(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
-    if (dtype == MNB_BF16 && !use_dw_stream(2, H, k) &&
+    if (dtype == MNB_BF16 &&
         (option_get(OPT_DW_MMA) == 2 || (option_get(OPT_DW_MMA) == 1 && H >= 12 && W >= 12 && C % 24 == 0))) {
         int r = dw_wgrad_mma(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
-        if (r != MNB_ERR_UNSUPPORTED) return r;
-    }
-    if (dtype == MNB_BF16 && use_dw_stream(2, H, k)) {
-        int r = dw_wgrad_stream(x, in_scale, in_shift, dz, dw, N, H, W, C, k, st);
         if (r != MNB_ERR_UNSUPPORTED) return r;
     }
     if (dtype == MNB_BF16) {

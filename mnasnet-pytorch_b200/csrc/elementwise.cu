@@ -20,12 +20,13 @@ void set_error(const char* fmt, ...) {
 }
 
 // kernel-selection switches: -1 = not set yet (the environment variable is consulted once, then the built-in default)
-static int g_opt[OPT_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
-static const char* const g_opt_name[OPT_COUNT] = {"pw_stream", "stem_mma", "dw_stream", "dw_stream_pd", "dw_stream_tw8",
-                                                   "dw_mma", "dw_mma_cg", "dw_mma_tws", "dw_mma_seg", "bn_ctas", "c3_mma", "dw_small", "pwb_slice", "pw_wide"};
-static const char* const g_opt_env[OPT_COUNT] = {"MNB_PW_STREAM", "MNB_STEM_MMA", "MNB_DW_STREAM", "MNB_DW_STREAM_PD", "MNB_DW_STREAM_TW8",
-                                                  "MNB_DW_MMA", "MNB_DW_MMA_CG", "MNB_DW_MMA_TWS", "MNB_DW_MMA_SEG", "MNB_BN_CTAS", "MNB_C3_MMA", "MNB_DW_SMALL", "MNB_PWB_SLICE", "MNB_PW_WIDE"};
-static const int g_opt_default[OPT_COUNT] = {1, 1, 0, 1, 0, 1, 0, 0, 0, 0, 1, 1, 0, 0};
+static int g_opt[OPT_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+static const char* const g_opt_name[OPT_COUNT] = {"pw_stream", "stem_mma", "dw_mma", "dw_mma_cg", "dw_mma_tws", "dw_mma_seg",
+                                                   "bn_ctas", "c3_mma", "dw_small", "pwb_slice", "pw_wide"};
+static const char* const g_opt_env[OPT_COUNT] = {"MNB_PW_STREAM", "MNB_STEM_MMA", "MNB_DW_MMA", "MNB_DW_MMA_CG", "MNB_DW_MMA_TWS",
+                                                  "MNB_DW_MMA_SEG", "MNB_BN_CTAS", "MNB_C3_MMA", "MNB_DW_SMALL", "MNB_PWB_SLICE",
+                                                  "MNB_PW_WIDE"};
+static const int g_opt_default[OPT_COUNT] = {1, 1, 1, 0, 0, 0, 0, 1, 1, 0, 0};
 int option_get(int id) {
     if (g_opt[id] < 0) {
         const char* e = getenv(g_opt_env[id]);

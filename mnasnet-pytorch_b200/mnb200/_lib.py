@@ -88,7 +88,7 @@ OPTION_EPOCH = 0        # bumped by set_option: captured CUDA graphs of a launch
 
 
 def set_option(name: str, value: int):
-    """Process-wide kernel-selection switch ("pw_stream", "stem_mma", "dw_stream"; include/mnb200.h)."""
+    """Process-wide kernel-selection switch ("pw_stream", "stem_mma", "dw_mma", "dw_small", ...; include/mnb200.h)."""
     global OPTION_EPOCH
     check(lib.mnb_set_option(name.encode(), int(value)), "set_option")
     OPTION_EPOCH += 1

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libmnb200.so")
-SOURCES = ["elementwise.cu", "dwconv.cu", "dwconv_tile.cu", "stem.cu", "conv_simt.cu", "gemm_tc.cu", "pw_stream.cu", "dwconv_stream.cu", "dw_mma.cu", "pw_bwd_fused.cu", "c3_mma.cu", "dw_small.cu", "stem_mma.cu", "pw_proj_bwd.cu", "pw_wide_fwd.cu"]
+SOURCES = ["elementwise.cu", "dwconv.cu", "dwconv_tile.cu", "stem.cu", "conv_simt.cu", "gemm_tc.cu", "pw_stream.cu", "dw_mma.cu", "pw_bwd_fused.cu", "c3_mma.cu", "dw_small.cu", "stem_mma.cu", "pw_proj_bwd.cu", "pw_wide_fwd.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -7,8 +7,6 @@ mkdir -p gpurun_out
 echo "== gpu tests ==";      timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 echo "== smoke ==";          timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 echo "== bench (1 GPU) ==";  timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --profile-out gpurun_out/kernel_table.json > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -c 600 gpurun_out/bench_1gpu.json
-echo "== depthwise row-stream sweep (prefetch depth 1/2/3, whole step tile / stream / auto) =="
-timeout 300 python scripts/exp_dw_stream.py > gpurun_out/exp_dw_stream.log 2>&1; tail -2 gpurun_out/exp_dw_stream.log | cut -c1-900
 echo "== 1x1 streaming vs tcgen05 =="
 timeout 300 python scripts/exp_stream.py pw_big stem_big net > gpurun_out/exp_stream.log 2>&1; tail -2 gpurun_out/exp_stream.log | cut -c1-600
 echo "== ncu launch list of one timed step (shares + DRAM bytes; never a bench value) =="

@@ -96,7 +96,7 @@ def test_dw_mma_forward_dgrad_wgrad(case, xform, forced_mma):
 def test_dw_fused_backward_matches_torch(case, act, small):
     """mnb_dw_bwd_fused vs the SURVEY appendix-F math in fp64: G = dA*[scale*z+shift>0]; dZ = a*G + b*z + c;
     dx = conv_dgrad(dZ); dw += conv_wgrad(A, dZ); dgamma/dbeta; reductions of dx for the producing block.
-    small = 0: the row-streaming kernel (dw_mma.cu) on every map; 2: the whole-tile kernel (dw_small.cu) on maps <= 28 rows."""
+    small = 0: the row-streaming kernel (dw_mma.cu) on every map; 2: the whole-tile kernel (dw_small.cu) on every map."""
     from mnb200 import _lib as L
     old_small = L.get_option("dw_small")
     L.set_option("dw_small", small)

@@ -157,15 +157,13 @@ def test_topk_and_meters():
 
 def test_kernel_selection_options():
     from mnb200 import _lib
-    assert (_lib.get_option("pw_stream"), _lib.get_option("stem_mma"), _lib.get_option("dw_stream")) == (1, 1, 0)
-    _lib.set_option("dw_stream", 1)
-    assert _lib.get_option("dw_stream") == 1
-    _lib.set_option("dw_stream", 0)
-    assert _lib.get_option("dw_stream") == 0
-    _lib.set_option("dw_stream", 2)
-    assert _lib.get_option("dw_stream") == 2
-    _lib.set_option("dw_stream", 0)
-    assert _lib.get_option("dw_stream_pd") == 1 and _lib.get_option("dw_stream_tw8") == 0
+    assert (_lib.get_option("pw_stream"), _lib.get_option("stem_mma"), _lib.get_option("dw_small"), _lib.get_option("pw_wide")) == (1, 1, 1, 0)
+    _lib.set_option("dw_small", 0)
+    assert _lib.get_option("dw_small") == 0
+    _lib.set_option("dw_small", 2)
+    assert _lib.get_option("dw_small") == 2
+    _lib.set_option("dw_small", 1)
+    assert _lib.get_option("dw_mma_tws") == 0 and _lib.get_option("c3_mma") == 1
     with pytest.raises(_lib.MnbError):
         _lib.set_option("no_such_option", 1)
 

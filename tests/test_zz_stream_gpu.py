@@ -175,66 +175,6 @@ def test_resume_restores_model_and_optimizer_state():
             assert torch.equal(a, b), k
 
 
-DW_STREAM_CASES = [(2, 12, 10, 32, 3, True), (2, 9, 11, 72, 5, True), (3, 7, 7, 48, 3, False), (2, 4, 4, 240, 5, True),
-                   (1, 17, 5, 1152, 3, True), (2, 14, 14, 576, 5, True), (2, 30, 20, 16, 5, False), (4, 56, 56, 72, 5, True)]
-
-
-@pytest.mark.parametrize("case", DW_STREAM_CASES)
-def test_depthwise_row_stream_kernels(case):
-    """bf16 depthwise forward (+BN statistics), backward-data and backward-weight through the register row-stream
-    kernels (option "dw_stream") vs torch fp64, and vs the shared-memory tile kernels they would replace."""
-    from test_ops_gpu import TOL, act, nchw, nhwc
-    from mnb200 import _lib as ML
-    L = _lib()
-    N, H, W, C, k, xform = case
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(N, C, H, W, generator=g, dtype=torch.float64)
-    w = (torch.randn(C, 1, k, k, generator=g, dtype=torch.float64) / k).float()
-    b = (torch.randn(C, generator=g, dtype=torch.float64) * 0.1).float()
-    s = (torch.rand(C, generator=g) + 0.5) if xform else None
-    t = (torch.randn(C, generator=g) * 0.3) if xform else None
-    xd = nhwc(x, "bf16")
-    x = nchw(xd)
-    a = act(x, s.double() if xform else None, t.double() if xform else None)
-    a_ = a.clone().requires_grad_(True)
-    w_ = w.double().requires_grad_(True)
-    zref = F.conv2d(a_, w_, b.double(), padding=k // 2, groups=C)
-    dz = torch.randn(N, C, H, W, generator=g, dtype=torch.float64)
-    dzd = nhwc(dz, "bf16")
-    zref.backward(nchw(dzd))
-    wd, bd = w.cuda(), b.cuda()
-    sd = s.cuda() if xform else None
-    td = t.cuda() if xform else None
-    res = {}
-    try:
-        for opt in (0, 1):
-            ML.set_option("dw_stream", opt)
-            z = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
-            stats = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
-            L.call("mnb_dw_fwd", P(xd), P(sd), P(td), P(wd), P(bd), P(z), P(stats), N, H, W, C, k, 1, stream())
-            dx = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
-            L.call("mnb_dw_dgrad", P(dzd), P(wd), P(dx), None, None, None, None, N, H, W, C, k, 1, stream())
-            dw = torch.zeros(C, 1, k, k, device="cuda")
-            for _ in range(2):
-                L.call("mnb_dw_wgrad", P(xd), P(sd), P(td), P(dzd), P(dw), N, H, W, C, k, 1, stream())
-            torch.cuda.synchronize()
-            res[opt] = (z, stats, dx, dw)
-    finally:
-        ML.set_option("dw_stream", 0)
-    z, stats, dx, dw = res[1]
-    assert torch.isfinite(z.float()).all() and torch.isfinite(dx.float()).all()
-    assert rel(nchw(z), zref) < TOL["bf16"]
-    zs = nchw(z)
-    torch.testing.assert_close(stats[:C].cpu(), zs.sum(dim=(0, 2, 3)), rtol=1e-5, atol=1e-4)
-    torch.testing.assert_close(stats[C:].cpu(), (zs * zs).sum(dim=(0, 2, 3)), rtol=1e-5, atol=1e-4)
-    assert rel(nchw(dx), a_.grad) < TOL["bf16"]
-    assert rel(dw, 2 * w_.grad) < TOL["bf16"]
-    # against the tile kernels: same bf16 operands; the row-stream kernel keeps the activated input in fp32 (the tile
-    # kernel re-rounds it to bf16), so outputs agree to bf16 rounding, not bit for bit
-    z0, stats0, dx0, dw0 = res[0]
-    assert rel(z.float(), z0.float()) < 5e-3 and rel(dx.float(), dx0.float()) < 5e-3 and rel(dw, dw0) < 5e-3
-
-
 @pytest.mark.parametrize("opt_name", ["sgd", "rmsprop"])
 def test_other_optimizers_match_torch(opt_name):
     """torch.optim.SGD / RMSprop with the reference's arguments (lr only, train.py:222-229) vs the flat
