@@ -8,12 +8,14 @@
 // issue (177 / 404 / 238 us for fwd / dgrad / wgrad of 16->24 at 112x112 against a 26 us HBM floor).  Here the im2col is
 // free: a CTA owns TH full output rows of one image; the (TH-1)*S+3 full input rows it needs are CONTIGUOUS in global
 // memory, so ONE 1-D bulk copy (cp.async.bulk, mbarrier completion) brings them into shared memory exactly as they lie
-// in HBM -- a 4-D TMA box with a 32..80-byte inner extent moves only ~7 B/clk/SM (measured: first version of this file,
-// 73 us for the 16->24 forward), the 1-D copy has no per-row cost.  relu(scale*x+shift) is applied in place, and
+// in HBM (no tensor maps; the first version of this file used 4-D TMA boxes with zero-filled halos and ran at the same
+// speed, 73 vs 69 us for the 16->24 forward: the copy is not the limit).  relu(scale*x+shift) is applied in place, and
 // ldmatrix reads the A fragments of every tap straight from that NHWC tile: row addresses are per lane, so the stride
 // between output pixels costs nothing and a tap that falls into the left / right padding simply points at a block of
 // zeros (rows above / below the image are zero-filled in shared memory).  mma.sync.m16n8k16 / m16n8k8 with the weights
 // resident in shared memory; the output tile is contiguous in global memory too and leaves through one bulk store.
+// What bounds it (ncu, 16->24 forward): shared-memory wavefronts -- the 8 rows of a stride-2 ldmatrix at a 32-byte pixel
+// pitch fall into two bank groups (4-way conflict, l1tex 75 %); three CTAs per SM: 54 / 46 / 78 us fwd / dgrad / wgrad.
 //   FWD    D[m = pixel][n = co]      += A[pixel + tap][k = ci] * W[co][tap][ci]
 //   DGRAD  by input-pixel parity class (py, px): D[m = (a, b)][n = ci] += dZ[(a + dy, b + dx)][k = co] * W[co][ci][tap],
 //          only the 1 / 2 / 2 / 4 taps with (py + 1 - ky), (px + 1 - kx) even contribute
