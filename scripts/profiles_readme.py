@@ -74,6 +74,19 @@ for r in nc:
     st = ", ".join(f"{a} {b:.1f}" for a, b in list(r["stalls_per_issue"].items())[:3])
     out.append(f"| `{k}` | {r['dur_us']:.0f} | {r['tensor_pipe_active_pct']:.1f} | {r['issue_active_pct']:.1f} | {r['warps_active_pct']:.1f} | {r['regs']:.0f} | "
                f"{r['smem_dyn_kb']:.0f} | {r['dram_read_mb'] + r['dram_write_mb']:.0f} | {st} |")
+nb = J("r2_ncu_gemm_dw_summary_backward.json")
+out.append("")
+out.append(f"### The same ncu pass over the BACKWARD half of a step ({len(nb)} launches, captured at the 15.09 ms build: same kernel code; since then every depthwise fused backward runs `dws_bwd_k`) -- `r2_ncu_gemm_dw_summary_backward.json`, kernels not in the table above")
+out.append("")
+out.append("| kernel | us | tensor pipe active % | issue active % | warps active % | regs | smem KB | DRAM MB (read + write) | top stalls per issue |")
+out.append("|---|---|---|---|---|---|---|---|---|")
+for r in nb:
+    k = r["kernel"].replace("void ", "").split("(")[0]
+    if k in seen: continue
+    seen.add(k)
+    st = ", ".join(f"{a} {b:.1f}" for a, b in list(r["stalls_per_issue"].items())[:3])
+    out.append(f"| `{k}` | {r['dur_us']:.0f} | {r['tensor_pipe_active_pct']:.1f} | {r['issue_active_pct']:.1f} | {r['warps_active_pct']:.1f} | {r['regs']:.0f} | "
+               f"{r['smem_dyn_kb']:.0f} | {r['dram_read_mb'] + r['dram_write_mb']:.0f} | {st} |")
 frag = "\n".join(out)
 p = os.path.join(R, "README.md")
 s = open(p).read()
