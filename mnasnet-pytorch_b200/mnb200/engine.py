@@ -745,12 +745,12 @@ class Plan:
         if ent is None:                       # first call: eager
             if len(self.prog_graphs) > 16:
                 self.prog_graphs.clear()
-            self.prog_graphs[key] = "warm"
+            self.prog_graphs[key] = ("warm", ops)       # holds the list: its id cannot be recycled by a rebuilt program
             if pre is not None:
                 pre()
             self.run(ops, stream)
             return
-        if ent == "warm":                     # second call: capture, then replay
+        if ent[0] == "warm":                  # second call: capture, then replay
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
